@@ -1,0 +1,95 @@
+/* metmhn_b200 -- C-ABI of the B200-native metMHN likelihood/gradient engine.
+ *
+ * The reference (cbg-ethz/metMHN) has no FFI layer: its training hot path sits behind the
+ * plain Python functions of metmhn/regularized_optimization.py.  This header is the boundary
+ * a maintainer binds (ctypes stub in INTEGRATION.md) to run that path on a B200:
+ *
+ *   reference call                                          replaced by
+ *   ------------------------------------------------------  ---------------------------
+ *   score_and_grad(...)      regularized_optimization.py:163   mmh_value_grad
+ *   score(...)               regularized_optimization.py:55    mmh_value
+ *   per-row _lp_* dispatch   regularized_optimization.py:75-119  mmh_per_patient
+ *   (dataset constant across L-BFGS iterations, :328)       mmh_create / mmh_destroy
+ *
+ * Plain pointers and sizes only.  All entry points return 0 on success or a negative
+ * MMH_E* code; mmh_last_error() gives a thread-local message.  There is no CPU fallback:
+ * without a CUDA device every compute entry point fails with MMH_ECUDA.
+ *
+ * Layouts (identical to the reference):
+ *   dat    : int8, n_dat rows of 2*n_mut+3 columns
+ *            [PT_0, MT_0, ..., PT_{n-1}, MT_{n-1}, seeding, order, type]   (:63-66)
+ *   params : double[(n+1)*(n+3)] = [log_theta row-major (n+1)^2, log_d_p (n+1), log_d_m (n+1)]
+ *            (:292-294); gradients use the same packing (:296).
+ */
+#ifndef METMHN_B200_H
+#define METMHN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMH_OK          0
+#define MMH_EINVAL    (-1)   /* bad shape, non-binary genotype, paired row without seeding, n_mut too large */
+#define MMH_ECUDA     (-2)   /* CUDA runtime failure or no device */
+#define MMH_ENOMEM    (-3)
+#define MMH_ETOOLARGE (-4)   /* a patient's restricted state space exceeds the supported size */
+
+#define MMH_MAX_MUT    28    /* events excluding seeding (LUAD uses 28) */
+#define MMH_MAX_BITS   26    /* largest restricted lattice (bits) one space may have */
+
+typedef struct mmh_handle mmh_handle;
+
+typedef struct mmh_stats_t {
+    int64_t n_dat;            /* rows given to mmh_create */
+    int64_t n_em;             /* sum of the seeding column (regularized_optimization.py:256) */
+    int64_t n_spaces;         /* lattices built (pre-seeding, joint, second-phase, unpaired) */
+    int64_t n_chunks;         /* scratch-sized batches the evaluation streams through */
+    int64_t n_launches;       /* kernel launches of the last evaluation */
+    double  states_value_grad;/* sum over spaces of N_eff */
+    double  alg_bytes;        /* 32 * sum N_eff : algorithmic bytes of one value+grad evaluation */
+    double  alg_flops;        /* sum N_eff * (2 k_eff + 4 c n_tot) */
+    double  exec_fma;         /* FP64 FMAs this implementation executes (estimate) */
+    double  last_ms;          /* device time of the last evaluation (CUDA events) */
+    double  scratch_bytes;    /* device scratch allocated */
+    int64_t k_hist[4][64];    /* [type][k] histogram of restricted sizes */
+} mmh_stats_t;
+
+/* Copy + preprocess the dataset (parse rows, canonical bit layout, bucket by lattice size,
+ * plan scratch chunks, upload).  `device` is the CUDA ordinal.  `chunk_bytes` bounds the
+ * scratch of one batch (0 = default). */
+int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_t n_dat, int64_t row_stride,
+               int device, int64_t chunk_bytes);
+
+/* score_and_grad: *score and grad[(n+1)(n+3)] as the reference returns them (means, weighted). */
+int mmh_value_grad(mmh_handle* h, const double* params, double perc_met, double* score, double* grad);
+
+/* score (value only; skips the adjoint pass). */
+int mmh_value(mmh_handle* h, const double* params, double perc_met, double* score);
+
+/* Same computation with caller-supplied class weights instead of the handle's own
+ * n_em / n_nm (used when the dataset is sharded over several handles / GPUs: every shard is
+ * scaled with the GLOBAL weights so that the shard results simply add up).
+ *   result = w_type0 * sum_{type 0} + w_other * sum_{types 1,2,3}
+ * out_host (1 + (n+1)(n+3) doubles: score, grad) and/or out_dev (same layout, device
+ * pointer on the handle's device, e.g. the buffer a NCCL all-reduce runs on) may be NULL.
+ * want_grad = 0 writes only out[0]. */
+int mmh_eval_weighted(mmh_handle* h, const double* params, double w_type0, double w_other,
+                      int want_grad, double* out_host, double* out_dev);
+
+/* Per-row log-likelihoods of the last evaluation's parameters (test hook).  Rows with an
+ * unknown type get 0. */
+int mmh_per_patient(mmh_handle* h, const double* params, double* logp);
+
+int mmh_stats(mmh_handle* h, mmh_stats_t* out);
+void mmh_destroy(mmh_handle* h);
+const char* mmh_last_error(void);
+/* Measured FP64 FMA throughput of the device in TFLOP/s (independent-DFMA micro-kernel);
+ * denominator for the FP64 roofline since MEASURED_PEAKS.json has none. */
+int mmh_measure_fp64_tflops(int device, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,148 @@
+"""ctypes binding of libmetmhn_b200.so (include/metmhn_b200.h).
+
+There is deliberately no fallback: if the shared library is missing, or the machine has no CUDA
+device, every compute call raises.  The oracle under /oracle is test infrastructure and is never
+imported from here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmetmhn_b200.so")
+
+MMH_OK, MMH_EINVAL, MMH_ECUDA, MMH_ENOMEM, MMH_ETOOLARGE = 0, -1, -2, -3, -4
+MAX_MUT = 28
+
+EXPORTS = ("mmh_create", "mmh_value_grad", "mmh_value", "mmh_eval_weighted", "mmh_per_patient",
+           "mmh_stats", "mmh_destroy", "mmh_last_error", "mmh_measure_fp64_tflops")
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_dat", C.c_int64), ("n_em", C.c_int64), ("n_spaces", C.c_int64), ("n_chunks", C.c_int64),
+                ("n_launches", C.c_int64), ("states_value_grad", C.c_double), ("alg_bytes", C.c_double),
+                ("alg_flops", C.c_double), ("exec_fma", C.c_double), ("last_ms", C.c_double),
+                ("scratch_bytes", C.c_double), ("k_hist", (C.c_int64 * 64) * 4)]
+
+
+class MetMHNError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"metmhn_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MetMHNError(MMH_ECUDA, f"{LIB_PATH} is not built (run `python -c 'import __graft_entry__ as g; "
+                                     "g.build()'` or `make -C metmhn_b200/csrc`); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    dp = C.POINTER(C.c_double)
+    L.mmh_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int64]
+    L.mmh_value_grad.argtypes = [C.c_void_p, dp, C.c_double, dp, dp]
+    L.mmh_value.argtypes = [C.c_void_p, dp, C.c_double, dp]
+    L.mmh_eval_weighted.argtypes = [C.c_void_p, dp, C.c_double, C.c_double, C.c_int, dp, C.c_void_p]
+    L.mmh_per_patient.argtypes = [C.c_void_p, dp, dp]
+    L.mmh_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    L.mmh_destroy.argtypes = [C.c_void_p]
+    L.mmh_destroy.restype = None
+    L.mmh_last_error.restype = C.c_char_p
+    L.mmh_measure_fp64_tflops.argtypes = [C.c_int, dp]
+    for name in EXPORTS:
+        if name not in ("mmh_destroy", "mmh_last_error"):
+            getattr(L, name).restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != MMH_OK:
+        raise MetMHNError(rc, lib().mmh_last_error().decode("utf-8", "replace"))
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class Handle:
+    """Device-resident, preprocessed dataset (one per GPU / shard)."""
+
+    def __init__(self, dat, device=0, chunk_bytes=0):
+        dat = np.ascontiguousarray(np.asarray(dat), dtype=np.int8)
+        if dat.ndim != 2 or dat.shape[1] < 5 or (dat.shape[1] - 3) % 2:
+            raise MetMHNError(MMH_EINVAL, "dat must be (n_dat, 2n+3) int8")
+        self.n_mut = (dat.shape[1] - 3) // 2
+        self.n_tot = self.n_mut + 1
+        self.npar = self.n_tot * (self.n_tot + 2)
+        self.n_dat = dat.shape[0]
+        self.device = device
+        self._h = C.c_void_p()
+        check(lib().mmh_create(C.byref(self._h), self.n_mut, dat.ctypes.data_as(C.c_void_p), dat.shape[0],
+                               dat.shape[1], device, int(chunk_bytes)))
+
+    def _params(self, params):
+        p = np.ascontiguousarray(np.asarray(params, dtype=np.float64).ravel())
+        if p.shape[0] != self.npar:
+            raise MetMHNError(MMH_EINVAL, f"params must have {(self.npar)} entries")
+        return p
+
+    def value_grad(self, params, perc_met):
+        p = self._params(params)
+        score = C.c_double()
+        grad = np.empty(self.npar)
+        check(lib().mmh_value_grad(self._h, _dptr(p), float(perc_met), C.byref(score), _dptr(grad)))
+        return score.value, grad
+
+    def value(self, params, perc_met):
+        p = self._params(params)
+        score = C.c_double()
+        check(lib().mmh_value(self._h, _dptr(p), float(perc_met), C.byref(score)))
+        return score.value
+
+    def eval_weighted(self, params, w_type0, w_other, want_grad=True, out_dev_ptr=None, to_host=True):
+        p = self._params(params)
+        out = np.empty(self.npar + 1) if to_host else None
+        check(lib().mmh_eval_weighted(self._h, _dptr(p), float(w_type0), float(w_other), int(bool(want_grad)),
+                                      _dptr(out) if to_host else None,
+                                      C.c_void_p(out_dev_ptr) if out_dev_ptr else None))
+        if not to_host:
+            return None
+        return (out[0], out[1:]) if want_grad else (out[0], None)
+
+    def per_patient(self, params):
+        p = self._params(params)
+        out = np.zeros(max(self.n_dat, 1))
+        check(lib().mmh_per_patient(self._h, _dptr(p), _dptr(out)))
+        return out[: self.n_dat]
+
+    def stats(self):
+        s = Stats()
+        check(lib().mmh_stats(self._h, C.byref(s)))
+        d = {k: getattr(s, k) for k, _ in Stats._fields_ if k != "k_hist"}
+        d["k_hist"] = {t: {k: int(s.k_hist[t][k]) for k in range(64) if s.k_hist[t][k]} for t in range(4)}
+        return d
+
+    def close(self):
+        if self._h:
+            lib().mmh_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def measure_fp64_tflops(device=0):
+    v = C.c_double()
+    check(lib().mmh_measure_fp64_tflops(device, C.byref(v)))
+    return v.value

@@ -1,0 +1,542 @@
+// Host side of libmetmhn_b200.so: dataset preprocessing (done once, the dataset is constant over the
+// L-BFGS iterations, regularized_optimization.py:328), scratch/chunk planning, the per-evaluation launch
+// sequence and the C-ABI of include/metmhn_b200.h.  No CPU fallback: every compute path is a CUDA kernel.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/metmhn_b200.h"
+#include "mmh_device.cuh"
+
+using namespace mmh;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(MMH_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));       \
+    } while (0)
+
+namespace {
+
+struct Range { uint64_t off = 0; uint32_t cnt = 0; };
+
+struct ChunkPlan {
+    uint64_t space0 = 0;
+    uint32_t nspaces = 0;
+    Range setup, pre, main_small, sec_small, logp, joints, st_a, st_b, fin;
+    std::vector<Range> main_lv, sec_lv;          // big-tier segments per popcount level
+    uint64_t scratch = 0;                        // doubles
+};
+
+struct PatientPlan {
+    std::vector<SpaceDev> sp;                    // links are local indices
+    uint64_t scratch = 0;
+};
+
+}  // namespace
+
+struct mmh_handle {
+    int device = 0, n = 0, n_tot = 0;
+    int64_t n_dat = 0, n_em = 0;
+    std::vector<ChunkPlan> chunks;
+    SpaceDev* d_spaces = nullptr;
+    uint32_t* d_lists = nullptr;
+    Item* d_items = nullptr;
+    uint32_t* d_hs = nullptr;
+    uint8_t* d_cls = nullptr;
+    double* d_cnt = nullptr;
+    EvalPar* d_par = nullptr;
+    double *d_params = nullptr, *d_scratch = nullptr, *d_logp = nullptr, *d_partial = nullptr;
+    double *d_diracc = nullptr, *d_tdir = nullptr, *d_out = nullptr, *h_out = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int fin_ctas = 0;
+    uint32_t max_joints = 0;
+    mmh_stats_t st{};
+};
+
+static uint64_t space_scratch(SpaceDev& s, uint64_t off)
+{
+    const uint64_t NA = 1ull << s.KA, NB = 1ull << s.KB, N = NA * NB;
+    auto take = [&](uint64_t len) { uint64_t o = off; off += (len + 3) & ~3ull; return o; };
+    s.tabA = take(NR * NA);
+    s.tabB = s.kind == K_JOINT ? take(NR * NB) : 0;
+    s.y_off = take(N);
+    s.x_off = take(N);
+    s.stA = s.stB = s.stP = 0;
+    s.slices = 1;
+    if (s.kind == K_JOINT) {
+        s.slices = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(1, NB / 64));
+        s.stA = take((s.KA + 1) * NA);
+        s.stB = take((s.KB + 1) * NB);
+        s.stP = take((uint64_t)s.slices * (s.KA + 1) * NA);
+    }
+    return off;
+}
+
+static int build_patient(const int8_t* row, int n, int32_t pid, PatientPlan& pp, mmh_stats_t& st,
+                         std::vector<double>& cnt_dm2, uint8_t& cls)
+{
+    const int n_tot = n + 1;
+    const int typ = row[2 * n + 2];
+    pp.sp.clear();
+    cls = 255;
+    for (int c = 0; c < 2 * n + 1; ++c)
+        if (row[c] != 0 && row[c] != 1) return fail(MMH_EINVAL, "genotype entries must be 0 or 1");
+    auto base = [&](Kind k) {
+        SpaceDev s{};
+        s.kind = k; s.n_tot = (uint8_t)n_tot; s.patient = pid; s.cls = (typ == 0) ? 0 : 1;
+        s.joint = s.pre = s.pf = s.mf = -1;
+        return s;
+    };
+    if (typ == 0 || typ == 1) {
+        SpaceDev s = base(K_S1);
+        int k = 0;
+        for (int j = 0; j < n_tot; ++j)
+            if (row[2 * j]) { if (k >= MAXG) return fail(MMH_ETOOLARGE, "unpaired patient with more than 16 events"); s.evA[k++] = (uint8_t)j; }
+        s.KA = (uint8_t)k;
+        st.k_hist[typ][k]++;
+        st.states_value_grad += std::ldexp(1.0, k);
+        st.alg_flops += std::ldexp(1.0, k) * (2.0 * k + 4.0 * n_tot);
+        pp.sp.push_back(s);
+        cls = (uint8_t)s.cls;
+    } else if (typ == 2) {
+        SpaceDev s = base(K_S2);
+        int k = 0;
+        for (int j = 0; j < n; ++j)
+            if (row[2 * j + 1]) { if (k >= MAXG - 1) return fail(MMH_ETOOLARGE, "unpaired patient with more than 16 events"); s.evA[k++] = (uint8_t)j; cnt_dm2[j] += 1.0; }
+        s.evA[k++] = (uint8_t)n;
+        cnt_dm2[n] += 1.0;
+        s.KA = (uint8_t)k;
+        st.k_hist[2][k]++;
+        st.states_value_grad += std::ldexp(1.0, k);
+        st.alg_flops += std::ldexp(1.0, k) * (2.0 * k + 4.0 * n_tot);
+        pp.sp.push_back(s);
+        cls = 1;
+    } else if (typ == 3) {
+        if (row[2 * n] != 1) return fail(MMH_EINVAL, "paired row (type 3) without the seeding bit");
+        int order = row[2 * n + 1];
+        SpaceDev j = base(K_JOINT), pre = base(K_PRE);
+        std::vector<int> both, ponly, monly;
+        for (int e = 0; e < n; ++e) {
+            if (row[2 * e] && row[2 * e + 1]) both.push_back(e);
+            else if (row[2 * e]) ponly.push_back(e);
+            else if (row[2 * e + 1]) monly.push_back(e);
+        }
+        const int nb = (int)both.size(), ka = nb + (int)ponly.size(), kb = nb + (int)monly.size();
+        if (ka > MAXG || kb > MAXG || ka + kb > MMH_MAX_BITS)
+            return fail(MMH_ETOOLARGE, "paired patient exceeds the supported lattice size");
+        for (int b = 0; b < nb; ++b) { j.evA[b] = j.evB[b] = pre.evA[b] = (uint8_t)both[b]; }
+        for (size_t b = 0; b < ponly.size(); ++b) j.evA[nb + b] = (uint8_t)ponly[b];
+        for (size_t b = 0; b < monly.size(); ++b) j.evB[nb + b] = (uint8_t)monly[b];
+        for (int e = 0; e < n; ++e) { if (row[2 * e]) j.ptmask |= 1u << e; if (row[2 * e + 1]) j.mtmask |= 1u << e; }
+        j.KA = (uint8_t)ka; j.KB = (uint8_t)kb; j.nb = (uint8_t)nb;
+        pre.KA = (uint8_t)nb; pre.nb = (uint8_t)nb;
+        j.has_pf = (order == 0 || order == 1);
+        j.has_mf = (order != 1);
+        // local indices: 0 = pre, 1 = joint, then pf / mf
+        pre.joint = 1; j.pre = 0;
+        pp.sp.push_back(pre);
+        pp.sp.push_back(j);
+        const int kj = ka + kb + 1;
+        st.k_hist[3][kj]++;
+        double neff = std::ldexp(1.0, ka + kb);
+        st.alg_flops += neff * (2.0 * (ka + kb) + 8.0 * n_tot);
+        if (j.has_pf) {
+            SpaceDev s = base(K_PF);
+            s.KA = (uint8_t)kb; std::memcpy(s.evA, j.evB, MAXG); s.joint = 1;
+            pp.sp[1].pf = (int32_t)pp.sp.size();
+            pp.sp.push_back(s);
+            neff += std::ldexp(1.0, kb);
+            st.alg_flops += std::ldexp(1.0, kb) * (2.0 * kb + 4.0 * n_tot);
+        }
+        if (j.has_mf) {
+            SpaceDev s = base(K_MF);
+            s.KA = (uint8_t)ka; std::memcpy(s.evA, j.evA, MAXG); s.joint = 1;
+            pp.sp[1].mf = (int32_t)pp.sp.size();
+            pp.sp.push_back(s);
+            neff += std::ldexp(1.0, ka);
+            st.alg_flops += std::ldexp(1.0, ka) * (2.0 * ka + 4.0 * n_tot);
+        }
+        st.states_value_grad += neff;
+        cls = 1;
+    }
+    uint64_t off = 0;
+    for (auto& s : pp.sp) off = space_scratch(s, off);
+    pp.scratch = off;
+    return MMH_OK;
+}
+
+extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_t n_dat, int64_t row_stride,
+                          int device, int64_t chunk_bytes)
+{
+    if (!out || !dat || n_mut < 1 || n_mut > MMH_MAX_MUT || n_dat < 0 || row_stride < 2 * n_mut + 3)
+        return fail(MMH_EINVAL, "mmh_create: bad arguments (n_mut must be 1..28, row_stride >= 2n+3)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+        return fail(MMH_ECUDA, "mmh_create: no usable CUDA device (this library has no CPU fallback)");
+    CK(cudaSetDevice(device));
+    mmh_handle* h = new mmh_handle();
+    h->device = device; h->n = n_mut; h->n_tot = n_mut + 1; h->n_dat = n_dat;
+    h->st.n_dat = n_dat;
+    const int n = n_mut;
+
+    // ---- parse rows into per-patient space plans ------------------------------------------------------
+    std::vector<PatientPlan> pats((size_t)n_dat);
+    std::vector<uint8_t> cls((size_t)std::max<int64_t>(n_dat, 1), 255);
+    std::vector<double> cnt_dm2(NR, 0.0);
+    for (int64_t p = 0; p < n_dat; ++p) {
+        const int8_t* row = dat + p * row_stride;
+        h->n_em += row[2 * n];
+        int rc = build_patient(row, n, (int32_t)p, pats[(size_t)p], h->st, cnt_dm2, cls[(size_t)p]);
+        if (rc != MMH_OK) { delete h; return rc; }
+    }
+    h->st.n_em = h->n_em;
+    h->st.alg_bytes = 32.0 * h->st.states_value_grad;
+
+    // ---- pack patients into scratch chunks (largest first) --------------------------------------------
+    std::vector<int64_t> order((size_t)n_dat);
+    for (int64_t p = 0; p < n_dat; ++p) order[(size_t)p] = p;
+    std::stable_sort(order.begin(), order.end(),
+                     [&](int64_t a, int64_t b) { return pats[(size_t)a].scratch > pats[(size_t)b].scratch; });
+    uint64_t budget = (uint64_t)((chunk_bytes > 0 ? chunk_bytes : (int64_t)1 << 30) / 8);
+    std::vector<SpaceDev> spaces;
+    std::vector<uint32_t> lists;
+    std::vector<Item> items;
+    std::vector<std::vector<uint32_t>> hs_tab(MMH_MAX_BITS);     // popcount-sorted block indices per K-5
+    std::vector<std::vector<uint32_t>> hs_lvl(MMH_MAX_BITS);
+    std::vector<uint64_t> hs_off(MMH_MAX_BITS, 0);
+    std::vector<uint32_t> hs_all;
+    auto need_hs = [&](int kh) {
+        if (!hs_tab[kh].empty()) return;
+        const uint32_t n_blk = 1u << kh;
+        std::vector<uint32_t> cntl(kh + 2, 0);
+        for (uint32_t v = 0; v < n_blk; ++v) cntl[__builtin_popcount(v) + 1]++;
+        for (int l = 0; l <= kh; ++l) cntl[l + 1] += cntl[l];
+        hs_lvl[kh] = cntl;
+        std::vector<uint32_t> pos(cntl.begin(), cntl.end() - 1);
+        hs_tab[kh].resize(n_blk);
+        for (uint32_t v = 0; v < n_blk; ++v) hs_tab[kh][pos[__builtin_popcount(v)]++] = v;
+        hs_off[kh] = hs_all.size();
+        hs_all.insert(hs_all.end(), hs_tab[kh].begin(), hs_tab[kh].end());
+    };
+
+    size_t cur = 0;
+    uint64_t max_scratch = 0;
+    while (cur < order.size()) {
+        ChunkPlan ck;
+        ck.space0 = spaces.size();
+        uint64_t used = 0;
+        size_t first = cur;
+        while (cur < order.size()) {
+            const PatientPlan& pp = pats[(size_t)order[cur]];
+            if (pp.sp.empty()) { ++cur; continue; }
+            if (used > 0 && used + pp.scratch > budget) break;
+            const uint32_t base_idx = (uint32_t)(spaces.size() - ck.space0);
+            for (SpaceDev s : pp.sp) {
+                s.y_off += used; s.x_off += used; s.tabA += used;
+                if (s.kind == K_JOINT) { s.tabB += used; s.stA += used; s.stB += used; s.stP += used; }
+                if (s.joint >= 0) s.joint += base_idx;
+                if (s.pre >= 0) s.pre += base_idx;
+                if (s.pf >= 0) s.pf += base_idx;
+                if (s.mf >= 0) s.mf += base_idx;
+                spaces.push_back(s);
+            }
+            used += pp.scratch;
+            ++cur;
+        }
+        (void)first;
+        ck.nspaces = (uint32_t)(spaces.size() - ck.space0);
+        ck.scratch = used;
+        max_scratch = std::max(max_scratch, used);
+        if (ck.nspaces == 0) continue;
+        // ---- work lists of this chunk -------------------------------------------------------------------
+        const SpaceDev* sp = spaces.data() + ck.space0;
+        auto list_of = [&](auto pred) {
+            Range r; r.off = lists.size();
+            for (uint32_t i = 0; i < ck.nspaces; ++i) if (pred(sp[i])) lists.push_back(i);
+            r.cnt = (uint32_t)(lists.size() - r.off);
+            return r;
+        };
+        auto is_main = [](const SpaceDev& s) { return s.kind == K_JOINT || s.kind == K_S1 || s.kind == K_S2; };
+        auto is_sec = [](const SpaceDev& s) { return s.kind == K_PF || s.kind == K_MF; };
+        auto bits = [](const SpaceDev& s) { return (int)s.KA + (int)s.KB; };
+        ck.pre = list_of([&](const SpaceDev& s) { return s.kind == K_PRE; });
+        ck.main_small = list_of([&](const SpaceDev& s) { return is_main(s) && bits(s) < BIGK; });
+        ck.sec_small = list_of([&](const SpaceDev& s) { return is_sec(s) && bits(s) < BIGK; });
+        ck.logp = list_of([&](const SpaceDev& s) { return is_main(s); });
+        ck.joints = list_of([&](const SpaceDev& s) { return s.kind == K_JOINT; });
+        h->max_joints = std::max(h->max_joints, ck.joints.cnt);
+        ck.setup.off = items.size();
+        for (uint32_t i = 0; i < ck.nspaces; ++i) {
+            items.push_back({i, 0u, 0u});
+            if (sp[i].kind == K_JOINT) items.push_back({i, 1u, 0u});
+        }
+        ck.setup.cnt = (uint32_t)(items.size() - ck.setup.off);
+        auto levels_of = [&](auto pred, std::vector<Range>& lv) {
+            int maxkh = -1;
+            for (uint32_t i = 0; i < ck.nspaces; ++i) if (pred(sp[i]) && bits(sp[i]) >= BIGK) maxkh = std::max(maxkh, bits(sp[i]) - 5);
+            if (maxkh < 0) return;
+            lv.resize(maxkh + 1);
+            for (int l = 0; l <= maxkh; ++l) {
+                lv[l].off = items.size();
+                for (uint32_t i = 0; i < ck.nspaces; ++i) {
+                    if (!pred(sp[i]) || bits(sp[i]) < BIGK) continue;
+                    const int kh = bits(sp[i]) - 5;
+                    if (l > kh) continue;
+                    need_hs(kh);
+                    const uint32_t a = hs_lvl[kh][l], b = hs_lvl[kh][l + 1];
+                    for (uint32_t r = a; r < b; r += SEGB)
+                        items.push_back({i, (uint32_t)(hs_off[kh] + r), std::min<uint32_t>(SEGB, b - r)});
+                }
+                lv[l].cnt = (uint32_t)(items.size() - lv[l].off);
+            }
+        };
+        levels_of(is_main, ck.main_lv);
+        levels_of(is_sec, ck.sec_lv);
+        ck.st_a.off = items.size();
+        for (uint32_t i = 0; i < ck.nspaces; ++i)
+            if (sp[i].kind == K_JOINT) {
+                const uint32_t nblk = std::max<uint32_t>(1u, (1u << sp[i].KA) >> 5);
+                for (uint32_t sl = 0; sl < sp[i].slices; ++sl)
+                    for (uint32_t b = 0; b < nblk; ++b) items.push_back({i, b, sl});
+            }
+        ck.st_a.cnt = (uint32_t)(items.size() - ck.st_a.off);
+        ck.st_b.off = items.size();
+        for (uint32_t i = 0; i < ck.nspaces; ++i)
+            if (sp[i].kind == K_JOINT)
+                for (uint32_t u = 0; u < (1u << sp[i].KB); u += 8) items.push_back({i, u, std::min<uint32_t>(8u, (1u << sp[i].KB) - u)});
+        ck.st_b.cnt = (uint32_t)(items.size() - ck.st_b.off);
+        ck.fin.off = items.size();
+        for (uint32_t i = 0; i < ck.nspaces; ++i) {
+            for (uint32_t u = 0; u < (1u << sp[i].KA); u += FIN_U) items.push_back({i, 0u, u});
+            if (sp[i].kind == K_JOINT)
+                for (uint32_t u = 0; u < (1u << sp[i].KB); u += FIN_U) items.push_back({i, 1u, u});
+        }
+        ck.fin.cnt = (uint32_t)(items.size() - ck.fin.off);
+        h->chunks.push_back(std::move(ck));
+    }
+    h->st.n_spaces = (int64_t)spaces.size();
+    h->st.n_chunks = (int64_t)h->chunks.size();
+
+    // ---- upload -----------------------------------------------------------------------------------------
+    cudaDeviceProp prop{};
+    CK(cudaGetDeviceProperties(&prop, device));
+    h->fin_ctas = prop.multiProcessorCount * 2;
+    auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(dst, std::max<size_t>(bytes, 16));
+        if (e != cudaSuccess) return e;
+        return bytes ? cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) : cudaSuccess;
+    };
+    CK(up((void**)&h->d_spaces, spaces.data(), spaces.size() * sizeof(SpaceDev)));
+    CK(up((void**)&h->d_lists, lists.data(), lists.size() * sizeof(uint32_t)));
+    CK(up((void**)&h->d_items, items.data(), items.size() * sizeof(Item)));
+    CK(up((void**)&h->d_hs, hs_all.data(), hs_all.size() * sizeof(uint32_t)));
+    CK(up((void**)&h->d_cls, cls.data(), cls.size()));
+    CK(up((void**)&h->d_cnt, cnt_dm2.data(), NR * sizeof(double)));
+    const size_t npar = (size_t)h->n_tot * (h->n_tot + 2);
+    CK(cudaMalloc((void**)&h->d_par, sizeof(EvalPar)));
+    CK(cudaMalloc((void**)&h->d_params, npar * sizeof(double)));
+    CK(cudaMalloc((void**)&h->d_scratch, std::max<uint64_t>(max_scratch, 4) * sizeof(double)));
+    CK(cudaMalloc((void**)&h->d_logp, std::max<int64_t>(n_dat, 1) * sizeof(double)));
+    CK(cudaMemset(h->d_logp, 0, std::max<int64_t>(n_dat, 1) * sizeof(double)));
+    CK(cudaMalloc((void**)&h->d_partial, (size_t)h->fin_ctas * NACC * NR * NR * sizeof(double)));
+    CK(cudaMalloc((void**)&h->d_diracc, 2 * NR * sizeof(double)));
+    CK(cudaMalloc((void**)&h->d_tdir, std::max<uint32_t>(h->max_joints, 1) * 2 * sizeof(double)));
+    CK(cudaMalloc((void**)&h->d_out, (npar + 1) * sizeof(double)));
+    CK(cudaMallocHost((void**)&h->h_out, (npar + 1) * sizeof(double)));
+    CK(cudaStreamCreate(&h->stream));
+    CK(cudaEventCreate(&h->ev0));
+    CK(cudaEventCreate(&h->ev1));
+    CK(cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * NACC * NR * NR * (int)sizeof(double)));
+    h->st.scratch_bytes = (double)max_scratch * 8.0;
+    *out = h;
+    return MMH_OK;
+}
+
+static int run_eval(mmh_handle* h, const double* params, double w0, double w1, int want_grad)
+{
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const size_t npar = (size_t)h->n_tot * (h->n_tot + 2);
+    int64_t launches = 0;
+    CK(cudaMemcpyAsync(h->d_params, params, npar * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(h->ev0, st));
+    k_prep<<<1, 1024, 0, st>>>(h->d_params, h->n_tot, h->d_par); ++launches;
+    if (want_grad) {
+        CK(cudaMemsetAsync(h->d_partial, 0, (size_t)h->fin_ctas * NACC * NR * NR * sizeof(double), st));
+        CK(cudaMemsetAsync(h->d_diracc, 0, 2 * NR * sizeof(double), st));
+    }
+    double* S = h->d_scratch;
+    for (const ChunkPlan& ck : h->chunks) {
+        const SpaceDev* sp = h->d_spaces + ck.space0;
+        auto small = [&](const Range& r, bool adj) {
+            if (!r.cnt) return;
+            const uint32_t grid = (r.cnt + 7) / 8;
+            if (adj) k_solve_small<true><<<grid, 256, 0, st>>>(sp, h->d_lists + r.off, r.cnt, S);
+            else     k_solve_small<false><<<grid, 256, 0, st>>>(sp, h->d_lists + r.off, r.cnt, S);
+            ++launches;
+        };
+        auto big = [&](const std::vector<Range>& lv, bool adj) {
+            const int L = (int)lv.size();
+            for (int q = 0; q < L; ++q) {
+                const Range& r = lv[adj ? L - 1 - q : q];
+                if (!r.cnt) continue;
+                if (adj) k_solve_big<true><<<r.cnt, 256, 0, st>>>(sp, h->d_items + r.off, h->d_hs, S);
+                else     k_solve_big<false><<<r.cnt, 256, 0, st>>>(sp, h->d_items + r.off, h->d_hs, S);
+                ++launches;
+            }
+        };
+        k_setup<<<ck.setup.cnt, 128, 0, st>>>(sp, h->d_items + ck.setup.off, h->d_par, S); ++launches;
+        small(ck.pre, false);
+        small(ck.main_small, false);
+        big(ck.main_lv, false);
+        small(ck.sec_small, false);
+        big(ck.sec_lv, false);
+        if (ck.logp.cnt) { k_logp<<<(ck.logp.cnt + 127) / 128, 128, 0, st>>>(sp, h->d_lists + ck.logp.off, ck.logp.cnt, S, h->d_logp); ++launches; }
+        if (!want_grad) continue;
+        small(ck.sec_small, true);
+        big(ck.sec_lv, true);
+        if (ck.joints.cnt) {
+            k_direct<<<(ck.joints.cnt + 7) / 8, 256, 0, st>>>(sp, h->d_lists + ck.joints.off, ck.joints.cnt, S, h->d_tdir);
+            k_direct_acc<<<dim3(h->n_tot, 2), 256, 0, st>>>(sp, h->d_lists + ck.joints.off, ck.joints.cnt, h->d_tdir, w1, h->d_diracc);
+            launches += 2;
+        }
+        small(ck.main_small, true);
+        big(ck.main_lv, true);
+        small(ck.pre, true);
+        if (ck.st_a.cnt) {
+            k_stats_a<<<(ck.st_a.cnt + 7) / 8, 256, 0, st>>>(sp, h->d_items + ck.st_a.off, ck.st_a.cnt, S);
+            k_stats_a_reduce<<<ck.joints.cnt, 256, 0, st>>>(sp, h->d_lists + ck.joints.off, S);
+            k_stats_b<<<ck.st_b.cnt, 256, 0, st>>>(sp, h->d_items + ck.st_b.off, S);
+            launches += 3;
+        }
+        k_finish<<<h->fin_ctas, 128, 4 * NACC * NR * NR * sizeof(double), st>>>(sp, h->d_items + ck.fin.off, ck.fin.cnt, S, w0, w1, h->d_partial);
+        ++launches;
+    }
+    k_final<<<1, 1024, 0, st>>>(h->d_partial, h->fin_ctas, h->d_diracc, h->d_logp, h->d_cls, h->n_dat, h->d_cnt, w0, w1,
+                                h->n_tot, want_grad, h->d_out);
+    ++launches;
+    CK(cudaEventRecord(h->ev1, st));
+    CK(cudaGetLastError());
+    h->st.n_launches = launches;
+    return MMH_OK;
+}
+
+static void class_weights(const mmh_handle* h, double perc_met, double& w0, double& w1)
+{
+    // regularized_optimization.py:256-262
+    const double n_em = (double)h->n_em, n_nm = (double)h->n_dat - n_em;
+    const double w = (n_em * n_nm != 0.0) ? perc_met * n_nm / ((1.0 - perc_met) * n_em) : 1.0;
+    const double n_full = w * n_em + n_nm;
+    w0 = 1.0 / n_full;
+    w1 = w / n_full;
+}
+
+extern "C" int mmh_eval_weighted(mmh_handle* h, const double* params, double w_type0, double w_other,
+                                 int want_grad, double* out_host, double* out_dev)
+{
+    if (!h || !params) return fail(MMH_EINVAL, "mmh_eval_weighted: null argument");
+    int rc = run_eval(h, params, w_type0, w_other, want_grad);
+    if (rc != MMH_OK) return rc;
+    const size_t len = want_grad ? (size_t)h->n_tot * (h->n_tot + 2) + 1 : 1;
+    if (out_dev) CK(cudaMemcpyAsync(out_dev, h->d_out, len * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if (out_host) CK(cudaMemcpyAsync(h->h_out, h->d_out, len * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->st.last_ms = ms;
+    if (out_host) std::memcpy(out_host, h->h_out, len * sizeof(double));
+    return MMH_OK;
+}
+
+extern "C" int mmh_value_grad(mmh_handle* h, const double* params, double perc_met, double* score, double* grad)
+{
+    if (!h || !params || !score || !grad) return fail(MMH_EINVAL, "mmh_value_grad: null argument");
+    double w0, w1;
+    class_weights(h, perc_met, w0, w1);
+    const size_t npar = (size_t)h->n_tot * (h->n_tot + 2);
+    std::vector<double> buf(npar + 1);
+    int rc = mmh_eval_weighted(h, params, w0, w1, 1, buf.data(), nullptr);
+    if (rc != MMH_OK) return rc;
+    *score = buf[0];
+    std::memcpy(grad, buf.data() + 1, npar * sizeof(double));
+    return MMH_OK;
+}
+
+extern "C" int mmh_value(mmh_handle* h, const double* params, double perc_met, double* score)
+{
+    if (!h || !params || !score) return fail(MMH_EINVAL, "mmh_value: null argument");
+    double w0, w1;
+    class_weights(h, perc_met, w0, w1);
+    return mmh_eval_weighted(h, params, w0, w1, 0, score, nullptr);
+}
+
+extern "C" int mmh_per_patient(mmh_handle* h, const double* params, double* logp)
+{
+    if (!h || !params || !logp) return fail(MMH_EINVAL, "mmh_per_patient: null argument");
+    double s;
+    int rc = mmh_eval_weighted(h, params, 1.0, 1.0, 0, &s, nullptr);
+    if (rc != MMH_OK) return rc;
+    if (h->n_dat) CK(cudaMemcpy(logp, h->d_logp, (size_t)h->n_dat * sizeof(double), cudaMemcpyDeviceToHost));
+    return MMH_OK;
+}
+
+extern "C" int mmh_stats(mmh_handle* h, mmh_stats_t* out)
+{
+    if (!h || !out) return fail(MMH_EINVAL, "mmh_stats: null argument");
+    *out = h->st;
+    return MMH_OK;
+}
+
+extern "C" void mmh_destroy(mmh_handle* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_spaces); cudaFree(h->d_lists); cudaFree(h->d_items); cudaFree(h->d_hs); cudaFree(h->d_cls);
+    cudaFree(h->d_cnt); cudaFree(h->d_par); cudaFree(h->d_params); cudaFree(h->d_scratch); cudaFree(h->d_logp);
+    cudaFree(h->d_partial); cudaFree(h->d_diracc); cudaFree(h->d_tdir); cudaFree(h->d_out);
+    if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    delete h;
+}
+
+extern "C" const char* mmh_last_error(void) { return g_err.c_str(); }
+
+extern "C" int mmh_measure_fp64_tflops(int device, double* tflops)
+{
+    if (!tflops) return fail(MMH_EINVAL, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+        return fail(MMH_ECUDA, "no usable CUDA device");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop{};
+    CK(cudaGetDeviceProperties(&prop, device));
+    double* d = nullptr;
+    CK(cudaMalloc((void**)&d, 8));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    const int grid = prop.multiProcessorCount * 8, iters = 1 << 15;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(a));
+        k_fp64_peak<<<grid, 256>>>(d, iters);
+        CK(cudaEventRecord(b));
+        CK(cudaEventSynchronize(b));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        best = std::max(best, (double)grid * 256.0 * 8.0 * 2.0 * iters / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+    *tflops = best;
+    return MMH_OK;
+}

@@ -1,0 +1,143 @@
+"""Drop-in mirror of the reference's `metmhn/regularized_optimization.py` call surface.
+
+Same names, argument meaning and packing as the reference (file:line cited per function); the
+per-patient likelihood and adjoint gradient run on the GPU through the C-ABI of
+include/metmhn_b200.h.  The dataset is preprocessed and uploaded once and cached, because SciPy's
+L-BFGS-B calls `score_and_grad_reg` with the same `dat` at every iteration
+(`regularized_optimization.py:328`).  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import zlib
+from typing import Callable
+
+import numpy as np
+
+from ._lib import Handle
+
+_CACHE: dict = {}
+_CACHE_MAX = 8
+
+
+def dataset_handle(dat, device: int = 0) -> Handle:
+    """Handle for `dat` on `device`, cached by content."""
+    if isinstance(dat, Handle):
+        return dat
+    a = np.ascontiguousarray(np.asarray(dat), dtype=np.int8)
+    key = (a.shape, zlib.crc32(a.view(np.uint8).reshape(-1)), device)
+    h = _CACHE.get(key)
+    if h is None:
+        if len(_CACHE) >= _CACHE_MAX:
+            _CACHE.pop(next(iter(_CACHE))).close()
+        h = _CACHE[key] = Handle(a, device=device)
+    return h
+
+
+def clear_cache():
+    while _CACHE:
+        _CACHE.popitem()[1].close()
+
+
+def _pack(log_theta, log_d_p, log_d_m):
+    return np.concatenate([np.asarray(log_theta, dtype=np.float64).ravel(),
+                           np.asarray(log_d_p, dtype=np.float64).ravel(),
+                           np.asarray(log_d_m, dtype=np.float64).ravel()])
+
+
+def _unpack(vec, n_total):
+    vec = np.asarray(vec, dtype=np.float64)
+    sq = n_total * n_total
+    return vec[:sq].reshape(n_total, n_total), vec[sq:sq + n_total], vec[sq + n_total:]
+
+
+# ---- penalties (host side, O(n^2); regularized_optimization.py:11-52) ---------------------------------
+
+def L1(theta, eps: float = 1e-05):
+    """Smoothed L1 norm; the diagonal of a matrix argument is not penalised (:11-18)."""
+    t = np.array(theta, dtype=np.float64)
+    if t.ndim == 2:
+        t[np.diag_indices(t.shape[0])] = 0.0
+    return np.sqrt(t * t + eps).sum()
+
+
+def L1_(theta, eps: float = 1e-05):
+    """Derivative of L1, flattened (:21-28)."""
+    t = np.array(theta, dtype=np.float64)
+    if t.ndim == 2:
+        t[np.diag_indices(t.shape[0])] = 0.0
+    t = t.ravel()
+    return t / np.sqrt(t * t + eps)
+
+
+def sym_penal(log_theta, eps: float = 1e-05):
+    """Symmetrised group penalty over the pairs (theta_ij, theta_ji) (:31-35)."""
+    t = np.array(log_theta, dtype=np.float64)
+    n = t.shape[0]
+    t[np.diag_indices(n)] = 0.0
+    pair = np.sqrt(t * t + t.T * t.T - t * t.T + eps)
+    return 0.5 * (pair.sum() - n * np.sqrt(eps))
+
+
+def sym_penal_(log_theta, eps: float = 1e-05):
+    """Derivative of sym_penal, flattened (:38-43)."""
+    t = np.array(log_theta, dtype=np.float64)
+    t[np.diag_indices(t.shape[0])] = 0.0
+    pair = np.sqrt(t * t + t.T * t.T - t * t.T + eps)
+    return ((2.0 * t - t.T) / (2.0 * pair)).ravel()
+
+
+def symmetric_penal(params, n_total: int, eps: float = 1e-05):
+    """(penalty, gradient) for the packed parameter vector (:46-52)."""
+    th, dp, dm = _unpack(params, n_total)
+    value = sym_penal(th, eps) + L1(dp, eps) + L1(dm, eps)
+    grad = np.concatenate([sym_penal_(th, eps), L1_(dp, eps), L1_(dm, eps)])
+    return value, grad
+
+
+# ---- likelihood (GPU) -----------------------------------------------------------------------------------
+
+def score(log_theta, log_d_p, log_d_m, dat, perc_met: float):
+    """Weighted mean log-likelihood of `dat` (reference :55-130)."""
+    return dataset_handle(dat).value(_pack(log_theta, log_d_p, log_d_m), perc_met)
+
+
+def score_and_grad(log_theta, log_d_p, log_d_m, dat, perc_met: float):
+    """(score, d_theta (n+1)x(n+1), d_d_p, d_d_m) -- BASELINE's "value_grad" (reference :163-267)."""
+    h = dataset_handle(dat)
+    s, g = h.value_grad(_pack(log_theta, log_d_p, log_d_m), perc_met)
+    gth, gdp, gdm = _unpack(g, h.n_tot)
+    return s, gth.copy(), gdp.copy(), gdm.copy()
+
+
+def score_reg(params, dat, perc_met: float, penal: Callable, w_penal: float):
+    """Negative penalised log-likelihood (reference :133-160)."""
+    h = dataset_handle(dat)
+    pen, _ = penal(params, h.n_tot)
+    return np.array(-h.value(params, perc_met) + w_penal * pen)
+
+
+def score_and_grad_reg(params, dat, perc_met: float, penal: Callable, w_penal: float):
+    """(f, g) handed to L-BFGS-B: -score + lambda*penalty and its gradient (reference :270-298)."""
+    h = dataset_handle(dat)
+    s, g = h.value_grad(params, perc_met)
+    pen, pen_ = penal(params, h.n_tot)
+    return np.array(-s + w_penal * pen), -g + w_penal * np.asarray(pen_)
+
+
+def learn_mhn(th_init, dp_init, dm_init, dat, perc_met: float, penal: Callable, w_penal: float,
+              opt_iter: int = 1e05, opt_ftol: float = 1e-04, opt_v: bool = True):
+    """Fit a metMHN with SciPy L-BFGS-B exactly as the reference drives it (reference :301-334)."""
+    import scipy.optimize as opt
+
+    h = dataset_handle(dat)
+    n_total = np.asarray(th_init).shape[0]
+    x0 = _pack(th_init, dp_init, dm_init)
+    options = {"maxiter": int(opt_iter), "ftol": opt_ftol}
+    try:
+        res = opt.minimize(fun=score_and_grad_reg, jac=True, x0=x0, method="L-BFGS-B",
+                           args=(h, perc_met, penal, w_penal), options=dict(options, disp=opt_v))
+    except (TypeError, ValueError):      # newer SciPy dropped the `disp` option of L-BFGS-B
+        res = opt.minimize(fun=score_and_grad_reg, jac=True, x0=x0, method="L-BFGS-B",
+                           args=(h, perc_met, penal, w_penal), options=options)
+    th, dp, dm = _unpack(res.x, n_total)
+    return th.copy(), dp.copy(), dm.copy()

@@ -1,0 +1,138 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the golden vectors of the
+unmodified reference and against the CPU oracle on seeded synthetic data."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+TOL = 1e-10          # relative, FP64 (BASELINE.json north_star)
+
+pytestmark = pytest.mark.gpu
+
+
+def _split(g, n_tot):
+    sq = n_tot * n_tot
+    return g[:sq].reshape(n_tot, n_tot), g[sq:sq + n_tot], g[sq + n_tot:]
+
+
+def _case(golden, c):
+    return tuple(golden[f"{c}/{k}"] for k in ("theta", "d_p", "d_m", "dat")) + (float(golden[f"{c}/perc_met"]),)
+
+
+def test_dataset_level_against_reference_golden(golden):
+    import metmhn_b200 as mm
+    for c in [str(x) for x in golden["cases"]]:
+        th, dp, dm, dat, pm = _case(golden, c)
+        s, g, a, b = mm.score_and_grad(th, dp, dm, dat, pm)
+        ref = golden[f"{c}/score"]
+        assert abs(s - ref) <= TOL * abs(ref), (c, s, ref)
+        assert rel_err(g, golden[f"{c}/g"]) <= TOL, c
+        assert rel_err(a, golden[f"{c}/gdp"]) <= TOL, c
+        assert rel_err(b, golden[f"{c}/gdm"]) <= TOL, c
+        assert abs(mm.score(th, dp, dm, dat, pm) - golden[f"{c}/score_only"]) <= TOL * abs(ref), c
+        if f"{c}/f_reg" in golden.files:
+            params = np.concatenate([th.ravel(), dp, dm])
+            lam = float(golden[f"{c}/w_penal"])
+            f, gr = mm.score_and_grad_reg(params, dat, pm, mm.symmetric_penal, lam)
+            assert abs(float(f) - golden[f"{c}/f_reg"]) <= TOL * abs(golden[f"{c}/f_reg"]), c
+            assert rel_err(gr, golden[f"{c}/g_reg"]) <= TOL, c
+            assert abs(float(mm.score_reg(params, dat, pm, mm.symmetric_penal, lam)) - golden[f"{c}/f_reg_only"]) <= 1e-10
+
+
+def test_every_patient_kind_against_reference_golden(golden):
+    """One handle per row: every kind, empty / ragged genotypes, the seeding-only paired rows that the
+    reference routes through one_event.py, the -99 order marker."""
+    from metmhn_b200 import Handle
+    for c in [str(x) for x in golden["cases"]]:
+        if f"{c}/row_logp" not in golden.files:
+            continue
+        th, dp, dm, dat, _ = _case(golden, c)
+        params = np.concatenate([th.ravel(), dp, dm])
+        n_tot = th.shape[0]
+        lp_all = Handle(dat).per_patient(params)
+        for r in range(dat.shape[0]):
+            h = Handle(dat[r:r + 1])
+            s, g = h.eval_weighted(params, 1.0, 1.0)
+            h.close()
+            ref = golden[f"{c}/row_logp"][r]
+            assert abs(s - ref) <= TOL * abs(ref), (c, r)
+            assert abs(lp_all[r] - ref) <= TOL * abs(ref), (c, r)
+            for got, key in zip(_split(g, n_tot), ("row_g", "row_gdp", "row_gdm")):
+                want = golden[f"{c}/{key}"][r]
+                if np.abs(want).max() == 0.0:
+                    assert np.abs(got).max() == 0.0, (c, r, key)
+                else:
+                    assert rel_err(got, want) <= TOL, (c, r, key)
+
+
+def test_synthetic_n10_against_oracle():
+    """BASELINE config 2 shape (n = 10, mixed paired / unpaired) at a size the oracle finishes quickly."""
+    import metmhn_b200 as mm
+    from metmhn_b200.simulate import syn_v1
+    from oracle import lattice_direct as ld
+    d = syn_v1(10, 300, 10001, max_joint_bits=15)
+    ep = d["eval_point"]
+    th, dp, dm = ep[:121].reshape(11, 11), ep[121:132], ep[132:]
+    s, g, a, b = mm.score_and_grad(th, dp, dm, d["dat"], 0.65)
+    s0, g0, a0, b0 = ld.score_and_grad(th, dp, dm, d["dat"], 0.65)
+    assert abs(s - s0) <= TOL * abs(s0)
+    assert rel_err(g, g0) <= TOL and rel_err(a, a0) <= TOL and rel_err(b, b0) <= TOL
+
+
+def test_big_tier_spaces_against_oracle():
+    """Spaces above the small/big tier boundary (level launches): n = 14, paired rows with 13..17 bits."""
+    from metmhn_b200 import Handle
+    from metmhn_b200.simulate import syn_v1
+    from oracle import lattice_direct as ld
+    d = syn_v1(14, 1500, 14014, max_joint_bits=18)
+    dat = d["dat"]
+    kj = dat[:, :29].sum(axis=1)
+    pick = np.concatenate([np.nonzero((dat[:, -1] == 3) & (kj >= 14) & (kj <= 18))[0][:5],
+                           np.nonzero((dat[:, -1] == 2) & (kj >= 12))[0][:2],
+                           np.nonzero((dat[:, -1] == 1) & (kj >= 13))[0][:2]])
+    assert len(pick) >= 5
+    ep = d["eval_point"]
+    th, dp, dm = ep[:225].reshape(15, 15), ep[225:240], ep[240:]
+    sub = np.ascontiguousarray(dat[pick])
+    h = Handle(sub)
+    lp = h.per_patient(ep)
+    s, g = h.eval_weighted(ep, 1.0, 1.0)
+    G = np.zeros(15 * 17)
+    S = 0.0
+    for r in range(sub.shape[0]):
+        out = ld.patient_value_grad(th, dp, dm, sub[r])
+        assert abs(lp[r] - out[1]) <= TOL * abs(out[1]), r
+        S += out[1]
+        G += np.concatenate([out[2].ravel(), out[3], out[4]])
+    assert abs(s - S) <= TOL * abs(S)
+    assert rel_err(g, G) <= TOL
+
+
+def test_chunking_and_repeatability():
+    """Small scratch chunks give the same numbers; repeated evaluations are bit-identical."""
+    from metmhn_b200 import Handle
+    from metmhn_b200.simulate import syn_v1
+    d = syn_v1(8, 400, 8123)
+    ep = d["eval_point"]
+    h1 = Handle(d["dat"])
+    h2 = Handle(d["dat"], chunk_bytes=1 << 16)
+    s1, g1 = h1.value_grad(ep, 0.65)
+    s1b, g1b = h1.value_grad(ep, 0.65)
+    s2, g2 = h2.value_grad(ep, 0.65)
+    assert s1 == s1b and np.array_equal(g1, g1b)
+    assert h2.stats()["n_chunks"] > h1.stats()["n_chunks"]
+    assert abs(s1 - s2) <= 1e-13 * abs(s1) and rel_err(g2, g1) <= 1e-12
+
+
+def test_error_paths():
+    from metmhn_b200 import Handle, MetMHNError
+    bad = np.zeros((1, 9), dtype=np.int8)
+    bad[0, -1] = 3                      # paired row without seeding
+    with pytest.raises(MetMHNError):
+        Handle(bad)
+    bad2 = np.zeros((1, 9), dtype=np.int8)
+    bad2[0, 0] = 2
+    with pytest.raises(MetMHNError):
+        Handle(bad2)
+    h = Handle(np.zeros((0, 9), dtype=np.int8))       # empty dataset is allowed
+    assert h.stats()["n_spaces"] == 0
