@@ -240,7 +240,7 @@ __device__ __forceinline__ void solve_block(const SpaceDev& sp, const SpaceDev* 
     double rl[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     if (valid) {
         double d = tA[(uint64_t)ROW_D * NA + (s & (NA - 1u))];
-        if (KB) d += tB[(uint64_t)ROW_D * NB + (s >> KA)];
+        if (sp.kind == K_JOINT) d += tB[(uint64_t)ROW_D * NB + (s >> KA)];   // also when KB == 0
         inv = 1.0 / d;
         acc = ADJ ? rhs_adj(sp, spaces, S, s) : rhs_fwd(sp, spaces, S, s);
         for (int a = 5; a < K; ++a) {
