@@ -31,7 +31,8 @@ struct Range { uint64_t off = 0; uint32_t cnt = 0; };
 struct ChunkPlan {
     uint64_t space0 = 0;
     uint32_t nspaces = 0;
-    Range setup, pre, main_small, sec_small, logp, joints, st_a, st_b, fin;
+    Range setup, setup_wide, pre, main_small, sec_small, logp, joints, st_a, st_b, fin;
+    bool wide = false;                           // some group has more than MAXT bits
     std::vector<Range> main_lv, sec_lv;          // big-tier segments per popcount level
     uint64_t scratch = 0;                        // doubles
 };
@@ -67,8 +68,14 @@ static uint64_t space_scratch(SpaceDev& s, uint64_t off)
 {
     const uint64_t NA = 1ull << s.KA, NB = 1ull << s.KB, N = NA * NB;
     auto take = [&](uint64_t len) { uint64_t o = off; off += (len + 3) & ~3ull; return o; };
-    s.tabA = take(NR * NA);
-    s.tabB = s.kind == K_JOINT ? take(NR * NB) : 0;
+    auto table = [&](int KG, uint8_t& split) {
+        if (KG <= MAXT) { split = 0; return take((uint64_t)NR << KG); }
+        split = (uint8_t)((KG + 1) / 2);             // rate(i,u) = T1[i][u_lo] * T2[i][u_hi] + three full vectors
+        return take(((uint64_t)NR << split) + ((uint64_t)NR << (KG - split)) + (3ull << KG));
+    };
+    s.splitA = s.splitB = 0;
+    s.tabA = table(s.KA, s.splitA);
+    s.tabB = s.kind == K_JOINT ? table(s.KB, s.splitB) : 0;
     s.y_off = take(N);
     s.x_off = take(N);
     s.stA = s.stB = s.stP = 0;
@@ -101,7 +108,7 @@ static int build_patient(const int8_t* row, int n, int32_t pid, PatientPlan& pp,
         SpaceDev s = base(K_S1);
         int k = 0;
         for (int j = 0; j < n_tot; ++j)
-            if (row[2 * j]) { if (k >= MAXG) return fail(MMH_ETOOLARGE, "unpaired patient with more than 16 events"); s.evA[k++] = (uint8_t)j; }
+            if (row[2 * j]) { if (k >= MMH_MAX_BITS) return fail(MMH_ETOOLARGE, "unpaired patient exceeds the supported lattice size"); s.evA[k++] = (uint8_t)j; }
         s.KA = (uint8_t)k;
         st.k_hist[typ][k]++;
         st.states_value_grad += std::ldexp(1.0, k);
@@ -112,7 +119,7 @@ static int build_patient(const int8_t* row, int n, int32_t pid, PatientPlan& pp,
         SpaceDev s = base(K_S2);
         int k = 0;
         for (int j = 0; j < n; ++j)
-            if (row[2 * j + 1]) { if (k >= MAXG - 1) return fail(MMH_ETOOLARGE, "unpaired patient with more than 16 events"); s.evA[k++] = (uint8_t)j; cnt_dm2[j] += 1.0; }
+            if (row[2 * j + 1]) { if (k >= MMH_MAX_BITS - 1) return fail(MMH_ETOOLARGE, "unpaired patient exceeds the supported lattice size"); s.evA[k++] = (uint8_t)j; cnt_dm2[j] += 1.0; }
         s.evA[k++] = (uint8_t)n;
         cnt_dm2[n] += 1.0;
         s.KA = (uint8_t)k;
@@ -132,7 +139,7 @@ static int build_patient(const int8_t* row, int n, int32_t pid, PatientPlan& pp,
             else if (row[2 * e + 1]) monly.push_back(e);
         }
         const int nb = (int)both.size(), ka = nb + (int)ponly.size(), kb = nb + (int)monly.size();
-        if (ka > MAXG || kb > MAXG || ka + kb > MMH_MAX_BITS)
+        if (ka + kb > MMH_MAX_BITS)
             return fail(MMH_ETOOLARGE, "paired patient exceeds the supported lattice size");
         for (int b = 0; b < nb; ++b) { j.evA[b] = j.evB[b] = pre.evA[b] = (uint8_t)both[b]; }
         for (size_t b = 0; b < ponly.size(); ++b) j.evA[nb + b] = (uint8_t)ponly[b];
@@ -235,7 +242,6 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
         ChunkPlan ck;
         ck.space0 = spaces.size();
         uint64_t used = 0;
-        size_t first = cur;
         while (cur < order.size()) {
             const PatientPlan& pp = pats[(size_t)order[cur]];
             if (pp.sp.empty()) { ++cur; continue; }
@@ -253,7 +259,6 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
             used += pp.scratch;
             ++cur;
         }
-        (void)first;
         ck.nspaces = (uint32_t)(spaces.size() - ck.space0);
         ck.scratch = used;
         max_scratch = std::max(max_scratch, used);
@@ -278,9 +283,19 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
         ck.setup.off = items.size();
         for (uint32_t i = 0; i < ck.nspaces; ++i) {
             items.push_back({i, 0u, 0u});
-            if (sp[i].kind == K_JOINT) items.push_back({i, 1u, 0u});
+            if (sp[i].splitA) { items.push_back({i, 0u, 1u}); ck.wide = true; }
+            if (sp[i].kind == K_JOINT) {
+                items.push_back({i, 1u, 0u});
+                if (sp[i].splitB) { items.push_back({i, 1u, 1u}); ck.wide = true; }
+            }
         }
         ck.setup.cnt = (uint32_t)(items.size() - ck.setup.off);
+        ck.setup_wide.off = items.size();
+        for (uint32_t i = 0; i < ck.nspaces; ++i) {
+            if (sp[i].splitA) for (uint32_t u = 0; u < (1u << sp[i].KA); u += 1024) items.push_back({i, 0u, u});
+            if (sp[i].splitB) for (uint32_t u = 0; u < (1u << sp[i].KB); u += 1024) items.push_back({i, 1u, u});
+        }
+        ck.setup_wide.cnt = (uint32_t)(items.size() - ck.setup_wide.off);
         auto levels_of = [&](auto pred, std::vector<Range>& lv) {
             int maxkh = -1;
             for (uint32_t i = 0; i < ck.nspaces; ++i) if (pred(sp[i]) && bits(sp[i]) >= BIGK) maxkh = std::max(maxkh, bits(sp[i]) - 5);
@@ -356,7 +371,8 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
     CK(cudaStreamCreate(&h->stream));
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
-    CK(cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * NACC * NR * NR * (int)sizeof(double)));
+    CK(cudaFuncSetAttribute(k_finish<MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * NACC * NR * NR * (int)sizeof(double)));
+    CK(cudaFuncSetAttribute(k_finish<MAXG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * NACC * NR * NR * (int)sizeof(double)));
     h->st.scratch_bytes = (double)max_scratch * 8.0;
     *out = h;
     return MMH_OK;
@@ -396,6 +412,7 @@ static int run_eval(mmh_handle* h, const double* params, double w0, double w1, i
             }
         };
         k_setup<<<ck.setup.cnt, 128, 0, st>>>(sp, h->d_items + ck.setup.off, h->d_par, S); ++launches;
+        if (ck.setup_wide.cnt) { k_setup_wide<<<ck.setup_wide.cnt, 1024, 0, st>>>(sp, h->d_items + ck.setup_wide.off, h->d_par, S); ++launches; }
         small(ck.pre, false);
         small(ck.main_small, false);
         big(ck.main_lv, false);
@@ -414,12 +431,16 @@ static int run_eval(mmh_handle* h, const double* params, double w0, double w1, i
         big(ck.main_lv, true);
         small(ck.pre, true);
         if (ck.st_a.cnt) {
-            k_stats_a<<<(ck.st_a.cnt + 7) / 8, 256, 0, st>>>(sp, h->d_items + ck.st_a.off, ck.st_a.cnt, S);
+            if (ck.wide) k_stats_a<MAXG><<<(ck.st_a.cnt + 7) / 8, 256, 0, st>>>(sp, h->d_items + ck.st_a.off, ck.st_a.cnt, S);
+            else         k_stats_a<MAXT><<<(ck.st_a.cnt + 7) / 8, 256, 0, st>>>(sp, h->d_items + ck.st_a.off, ck.st_a.cnt, S);
             k_stats_a_reduce<<<ck.joints.cnt, 256, 0, st>>>(sp, h->d_lists + ck.joints.off, S);
-            k_stats_b<<<ck.st_b.cnt, 256, 0, st>>>(sp, h->d_items + ck.st_b.off, S);
+            if (ck.wide) k_stats_b<MAXG><<<ck.st_b.cnt, 256, 0, st>>>(sp, h->d_items + ck.st_b.off, S);
+            else         k_stats_b<MAXT><<<ck.st_b.cnt, 256, 0, st>>>(sp, h->d_items + ck.st_b.off, S);
             launches += 3;
         }
-        k_finish<<<h->fin_ctas, 128, 4 * NACC * NR * NR * sizeof(double), st>>>(sp, h->d_items + ck.fin.off, ck.fin.cnt, S, w0, w1, h->d_partial);
+        const size_t fin_smem = 4 * NACC * NR * NR * sizeof(double);
+        if (ck.wide) k_finish<MAXG><<<h->fin_ctas, 128, fin_smem, st>>>(sp, h->d_items + ck.fin.off, ck.fin.cnt, S, w0, w1, h->d_partial);
+        else         k_finish<MAXT><<<h->fin_ctas, 128, fin_smem, st>>>(sp, h->d_items + ck.fin.off, ck.fin.cnt, S, w0, w1, h->d_partial);
         ++launches;
     }
     k_final<<<1, 1024, 0, st>>>(h->d_partial, h->fin_ctas, h->d_diracc, h->d_logp, h->d_cls, h->n_dat, h->d_cnt, w0, w1,

@@ -19,7 +19,8 @@ constexpr int NR      = 32;   // table rows per group (events 0..28, then the th
 constexpr int ROW_D   = 29;   // full diagonal part of the group  (D_g + outflow)
 constexpr int ROW_DP  = 30;   // PT-diagnosis rate table of the group (0 where it does not apply)
 constexpr int ROW_DM  = 31;   // MT-diagnosis rate table
-constexpr int MAXG    = 16;   // bits per group with explicit tables
+constexpr int MAXT    = 16;   // bits per group with one explicit table; wider groups use a product of two tables
+constexpr int MAXG    = 26;   // bits per group
 constexpr int BIGK    = 13;   // spaces with K >= BIGK are solved by per-level launches
 constexpr int SEGB    = 32;   // blocks of 32 states per big-tier segment (one CTA)
 constexpr int FIN_U   = 256;  // sub-states per finish work item
@@ -33,7 +34,8 @@ struct SpaceDev {
     int32_t  joint, pre, pf, mf;     // linked spaces (index into the chunk's space array), -1 = none
     uint32_t ptmask, mtmask;         // joint only: events present in PT / MT
     uint32_t slices;                 // joint only: partial-sum slices of the group-A statistics
-    uint32_t pad;
+    uint8_t  splitA, splitB;         // 0, or the number of low bits held by the first of two product tables
+    uint8_t  pad[2];
     uint64_t y_off, x_off;           // scratch offsets (in doubles)
     uint64_t tabA, tabB;             // NR x NA and NR x NB rate / diagonal tables
     uint64_t stA, stB, stP;          // joint only: marginal statistics ((KA+1) x NA, (KB+1) x NB, partials)
@@ -47,6 +49,35 @@ struct EvalPar {                     // recomputed from the parameter vector at 
 };
 
 struct Item { uint32_t space, a, b; };
+
+// A group's tables.  Narrow group (KG <= MAXT): one NR x NG table whose rows 29..31 hold the diagonal part
+// and the two diagnosis-rate tables.  Wide group: rate(i, u) = T1[i][u_lo] * T2[i][u_hi] (the rates are
+// products over the set bits, so they factor over any split of the bits) and the three special rows are
+// stored as full vectors behind the two tables.
+struct Side {
+    const double* t;
+    int KG, K1;
+    __device__ __forceinline__ uint32_t NG() const { return 1u << KG; }
+    __device__ __forceinline__ double rate(int row, uint32_t u) const {
+        if (K1 == 0) return t[((uint64_t)row << KG) + u];
+        const int K2 = KG - K1;
+        return t[((uint64_t)row << K1) + (u & ((1u << K1) - 1u))] *
+               t[((uint64_t)NR << K1) + ((uint64_t)row << K2) + (u >> K1)];
+    }
+    __device__ __forceinline__ double special(int row, uint32_t u) const {
+        if (K1 == 0) return t[((uint64_t)row << KG) + u];
+        const int K2 = KG - K1;
+        return t[((uint64_t)NR << K1) + ((uint64_t)NR << K2) + ((uint64_t)(row - ROW_D) << KG) + u];
+    }
+};
+__device__ __forceinline__ Side side_of(const SpaceDev& sp, int g, const double* S)
+{
+    Side v;
+    v.t = S + (g ? sp.tabB : sp.tabA);
+    v.KG = g ? sp.KB : sp.KA;
+    v.K1 = g ? sp.splitB : sp.splitA;
+    return v;
+}
 
 // ------------------------------------------------------------------------------------------
 __global__ void k_prep(const double* __restrict__ params, int n_tot, EvalPar* __restrict__ P)
@@ -88,71 +119,127 @@ __global__ void k_prep(const double* __restrict__ params, int n_tot, EvalPar* __
 //   T[i][u] = base_i * prod_{b in u, ev(b) != i} W[i][ev(b)]          (rate of event i in sub-state u)
 //   T[ROW_D][u] = D_g(u) + sum_{i not in u} T[i][u]                    (group part of diag(D - Q))
 // which is what kron_diag / diag_scal_* / the k* factor products of kronvec.py:713-999 evaluate
-// one shuffle pass at a time.  One CTA per (space, group).
+// one shuffle pass at a time.  One CTA per (space, group, part); part 1 is the high-bit factor table of a
+// wide group (no base rate, bits K1..KG-1).
+struct SetupSel { int wid, bid, nrows, dg; };
+__device__ __forceinline__ SetupSel setup_sel(const SpaceDev& sp, int g)
+{
+    const int n_tot = sp.n_tot, n = n_tot - 1;
+    switch (sp.kind) {                        // dg: 0 one, 1 DP0, 2 DPA, 3 DMB, 4 S2 mixed
+        case K_PRE:   return {0, 0, n_tot, 1};
+        case K_JOINT: return {0, g ? 1 : 0, n, g ? 3 : 2};
+        case K_PF:    return {2, 2, n, 0};
+        case K_MF:    return {1, 3, n, 0};
+        case K_S1:    return {1, 0, n_tot, 0};
+        default:      return {0, 0, n_tot, 4};
+    }
+}
+
+// D_g(u) and the two diagnosis tables of sub-state u (kronvec.py:574-602, 646-671; vanilla.py:125-142)
+__device__ __forceinline__ void diag_rates(int dg, int KG, const uint8_t* sev, int n, const EvalPar* __restrict__ P,
+                                           uint32_t u, double& d, double& vdp, double& vdm)
+{
+    d = 1.0; vdp = 0.0; vdm = 0.0;
+    if (dg == 1 || dg == 2) {
+        d = (dg == 2) ? P->dp[n] : 1.0;
+        for (int b = 0; b < KG; ++b) if ((u >> b) & 1u) d *= P->dp[sev[b]];
+        vdp = d;
+    } else if (dg == 3) {
+        d = P->dm[n];
+        for (int b = 0; b < KG; ++b) if ((u >> b) & 1u) d *= P->dm[sev[b]];
+        vdm = d;
+    } else if (dg == 4) {                                   // seeding is the top bit
+        const bool seeded = (u >> (KG - 1)) & 1u;
+        for (int b = 0; b < KG; ++b) if ((u >> b) & 1u) d *= seeded ? P->dm[sev[b]] : P->dp[sev[b]];
+        if (seeded) vdm = d; else vdp = d;
+    }
+}
+
 __global__ void k_setup(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items,
                         const EvalPar* __restrict__ P, double* __restrict__ S)
 {
     const Item it = items[blockIdx.x];
     const SpaceDev& sp = spaces[it.space];
-    const int g = it.a;
+    const int g = it.a, part = it.b;
     const int KG = g ? sp.KB : sp.KA;
-    const uint32_t NG = 1u << KG;
-    const uint8_t* ev = g ? sp.evB : sp.evA;
-    double* tab = S + (g ? sp.tabB : sp.tabA);
-    const int n_tot = sp.n_tot, n = n_tot - 1;
-    int wid = 0, bid = 0, nrows = n, dg = 0;   // dg: 0 one, 1 DP0, 2 DPA, 3 DMB, 4 S2 mixed
-    switch (sp.kind) {
-        case K_PRE:   wid = 0; bid = 0; nrows = n_tot; dg = 1; break;
-        case K_JOINT: wid = 0; bid = g ? 1 : 0; nrows = n; dg = g ? 3 : 2; break;
-        case K_PF:    wid = 2; bid = 2; nrows = n; dg = 0; break;
-        case K_MF:    wid = 1; bid = 3; nrows = n; dg = 0; break;
-        case K_S1:    wid = 1; bid = 0; nrows = n_tot; dg = 0; break;
-        default:      wid = 0; bid = 0; nrows = n_tot; dg = 4; break;
-    }
+    const int K1 = g ? sp.splitB : sp.splitA;
+    const int b0 = part ? K1 : 0;                           // first bit of this table
+    const int KT = K1 ? (part ? KG - K1 : K1) : KG;         // bits of this table
+    const uint32_t NT = 1u << KT;
+    const uint8_t* ev = (g ? sp.evB : sp.evA) + b0;
+    double* tab = S + (g ? sp.tabB : sp.tabA) + (part ? ((uint64_t)NR << K1) : 0);
+    const int n = sp.n_tot - 1;
+    const SetupSel sel = setup_sel(sp, g);
     __shared__ uint8_t sev[MAXG];
-    if (threadIdx.x < MAXG) sev[threadIdx.x] = ev[threadIdx.x];
+    if (threadIdx.x < MAXG) sev[threadIdx.x] = threadIdx.x < KT ? ev[threadIdx.x] : 255;
     __syncthreads();
-    for (uint32_t u = threadIdx.x; u < NG; u += blockDim.x) {
+    for (uint32_t u = threadIdx.x; u < NT; u += blockDim.x) {
         double dsum = 0.0;
-        for (int i = 0; i < nrows; ++i) {
-            double r = P->base[bid][i];
+        for (int i = 0; i < sel.nrows; ++i) {
+            double r = part ? 1.0 : P->base[sel.bid][i];
             bool in_u = false;
-            for (int b = 0; b < KG; ++b)
+            for (int b = 0; b < KT; ++b)
                 if ((u >> b) & 1u) {
-                    int e = sev[b];
-                    if (e == i) in_u = true; else r *= P->W[wid][i][e];
+                    const int e = sev[b];
+                    if (e == i) in_u = true; else r *= P->W[sel.wid][i][e];
                 }
-            tab[(uint64_t)i * NG + u] = r;
+            tab[(uint64_t)i * NT + u] = r;
             if (!in_u) dsum += r;
         }
-        double d = 1.0, vdp = 0.0, vdm = 0.0;
-        if (dg == 1 || dg == 2) {
-            d = (dg == 2) ? P->dp[n] : 1.0;
-            for (int b = 0; b < KG; ++b) if ((u >> b) & 1u) d *= P->dp[sev[b]];
-            vdp = d;
-        } else if (dg == 3) {
-            d = P->dm[n];
-            for (int b = 0; b < KG; ++b) if ((u >> b) & 1u) d *= P->dm[sev[b]];
-            vdm = d;
-        } else if (dg == 4) {                               // vanilla.py:125-142 (scal_d_pt); seeding is the top bit
-            const bool seeded = (u >> (KG - 1)) & 1u;
-            d = 1.0;
-            for (int b = 0; b < KG; ++b) if ((u >> b) & 1u) d *= seeded ? P->dm[sev[b]] : P->dp[sev[b]];
-            if (seeded) vdm = d; else vdp = d;
+        if (K1 == 0) {
+            double d, vdp, vdm;
+            diag_rates(sel.dg, KG, sev, n, P, u, d, vdp, vdm);
+            tab[(uint64_t)ROW_D * NT + u]  = d + dsum;
+            tab[(uint64_t)ROW_DP * NT + u] = vdp;
+            tab[(uint64_t)ROW_DM * NT + u] = vdm;
         }
-        tab[(uint64_t)ROW_D * NG + u]  = d + dsum;
-        tab[(uint64_t)ROW_DP * NG + u] = vdp;
-        tab[(uint64_t)ROW_DM * NG + u] = vdm;
     }
 }
 
+// special-row vectors of a wide group (after both factor tables exist); item.b = first sub-state of 1024
+__global__ void k_setup_wide(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items,
+                             const EvalPar* __restrict__ P, double* __restrict__ S)
+{
+    const Item it = items[blockIdx.x];
+    const SpaceDev& sp = spaces[it.space];
+    const int g = it.a;
+    const Side sd = side_of(sp, g, S);
+    const int KG = sd.KG, K1 = sd.K1, K2 = KG - K1;
+    const uint8_t* ev = g ? sp.evB : sp.evA;
+    const int n = sp.n_tot - 1;
+    const SetupSel sel = setup_sel(sp, g);
+    __shared__ uint8_t sev[MAXG];
+    __shared__ int8_t bit_of[NR];
+    if (threadIdx.x < NR) bit_of[threadIdx.x] = -1;
+    __syncthreads();
+    if (threadIdx.x < MAXG) {
+        sev[threadIdx.x] = threadIdx.x < KG ? ev[threadIdx.x] : 255;
+        if ((int)threadIdx.x < KG) bit_of[ev[threadIdx.x]] = (int8_t)threadIdx.x;
+    }
+    __syncthreads();
+    double* vec = S + (g ? sp.tabB : sp.tabA) + ((uint64_t)NR << K1) + ((uint64_t)NR << K2);
+    const uint32_t NG = 1u << KG;
+    const uint32_t u = it.b + threadIdx.x;
+    if (u >= NG) return;
+    double dsum = 0.0;
+    for (int i = 0; i < sel.nrows; ++i) {
+        const int b = bit_of[i];
+        if (b >= 0 && ((u >> b) & 1u)) continue;
+        dsum += sd.rate(i, u);
+    }
+    double d, vdp, vdm;
+    diag_rates(sel.dg, KG, sev, n, P, u, d, vdp, vdm);
+    vec[u] = d + dsum;
+    vec[(uint64_t)NG + u] = vdp;
+    vec[2ull * NG + u] = vdm;
+}
+
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ double rate_of(const SpaceDev& sp, const double* __restrict__ tA,
-                                          const double* __restrict__ tB, int a, uint32_t s)
+__device__ __forceinline__ double rate_of(const SpaceDev& sp, const Side& A, const Side& B, int a, uint32_t s)
 {
     const int KA = sp.KA;
-    if (a < KA) return tA[((uint64_t)sp.evA[a] << KA) + (s & ((1u << KA) - 1u))];
-    return tB[((uint64_t)sp.evB[a - KA] << sp.KB) + (s >> KA)];
+    if (a < KA) return A.rate(sp.evA[a], s & ((1u << KA) - 1u));
+    return B.rate(sp.evB[a - KA], s >> KA);
 }
 
 // right-hand side of the forward solve at state s
@@ -164,19 +251,18 @@ __device__ __forceinline__ double rhs_fwd(const SpaceDev& sp, const SpaceDev* __
             const uint32_t uA = s & ((1u << sp.KA) - 1u), uB = s >> sp.KA;
             if (uA != uB || uA >= (1u << sp.nb)) return 0.0;
             const SpaceDev& pre = spaces[sp.pre];            // seeding inflow from the pre-seeding lattice
-            const uint32_t N0 = 1u << pre.KA;
-            return S[pre.tabA + (uint64_t)(pre.n_tot - 1) * N0 + uA] * S[pre.y_off + uA];
+            return side_of(pre, 0, S).rate(pre.n_tot - 1, uA) * S[pre.y_off + uA];
         }
         case K_PF: {                                         // PT observed first: D_P y on states with every PT bit set
             const SpaceDev& j = spaces[sp.joint];
             const uint32_t NAj = 1u << j.KA;
-            const double cP = S[j.tabA + (uint64_t)ROW_DP * NAj + (NAj - 1u)];
+            const double cP = side_of(j, 0, S).special(ROW_DP, NAj - 1u);
             return cP * S[j.y_off + (((uint64_t)s << j.KA) | (NAj - 1u))];
         }
         case K_MF: {
             const SpaceDev& j = spaces[sp.joint];
             const uint32_t NBj = 1u << j.KB;
-            const double cM = S[j.tabB + (uint64_t)ROW_DM * NBj + (NBj - 1u)];
+            const double cM = side_of(j, 1, S).special(ROW_DM, NBj - 1u);
             return cM * S[j.y_off + (((uint64_t)(NBj - 1u) << j.KA) | s)];
         }
         default: return s == 0u ? 1.0 : 0.0;
@@ -207,15 +293,14 @@ __device__ __forceinline__ double rhs_adj(const SpaceDev& sp, const SpaceDev* __
             const uint32_t uA = s & (NA - 1u), uB = s >> sp.KA;
             double q = 0.0;
             if (sp.has_pf && uA == NA - 1u)
-                q += S[sp.tabA + (uint64_t)ROW_DP * NA + uA] * S[spaces[sp.pf].x_off + uB];
+                q += side_of(sp, 0, S).special(ROW_DP, uA) * S[spaces[sp.pf].x_off + uB];
             if (sp.has_mf && uB == NB - 1u)
-                q += S[sp.tabB + (uint64_t)ROW_DM * NB + uB] * S[spaces[sp.mf].x_off + uA];
+                q += side_of(sp, 1, S).special(ROW_DM, uB) * S[spaces[sp.mf].x_off + uA];
             return q;
         }
         default: {                                           // K_PRE: seeding edge into the joint lattice
             const SpaceDev& j = spaces[sp.joint];
-            const uint32_t N0 = 1u << sp.KA;
-            return S[sp.tabA + (uint64_t)(sp.n_tot - 1) * N0 + s] * S[j.x_off + (((uint64_t)s << j.KA) | s)];
+            return side_of(sp, 0, S).rate(sp.n_tot - 1, s) * S[j.x_off + (((uint64_t)s << j.KA) | s)];
         }
     }
 }
@@ -229,18 +314,17 @@ __device__ __forceinline__ void solve_block(const SpaceDev& sp, const SpaceDev* 
                                             double* __restrict__ S, uint32_t hi, int lane)
 {
     const int KA = sp.KA, KB = sp.KB, K = KA + KB;
-    const uint32_t N = 1u << K, NA = 1u << KA, NB = 1u << KB;
+    const uint32_t N = 1u << K, NA = 1u << KA;
     const uint32_t s = (hi << 5) | (uint32_t)lane;
     const bool valid = s < N;
-    const double* tA = S + sp.tabA;
-    const double* tB = S + sp.tabB;
+    const Side tA = side_of(sp, 0, S), tB = side_of(sp, 1, S);
     double* v = S + (ADJ ? sp.x_off : sp.y_off);
     const int nl = K < 5 ? K : 5;
     double acc = 0.0, inv = 0.0;
     double rl[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     if (valid) {
-        double d = tA[(uint64_t)ROW_D * NA + (s & (NA - 1u))];
-        if (sp.kind == K_JOINT) d += tB[(uint64_t)ROW_D * NB + (s >> KA)];   // also when KB == 0
+        double d = tA.special(ROW_D, s & (NA - 1u));
+        if (sp.kind == K_JOINT) d += tB.special(ROW_D, s >> KA);             // also when KB == 0
         inv = 1.0 / d;
         acc = ADJ ? rhs_adj(sp, spaces, S, s) : rhs_fwd(sp, spaces, S, s);
         for (int a = 5; a < K; ++a) {
@@ -334,7 +418,7 @@ __global__ void k_logp(const SpaceDev* __restrict__ spaces, const uint32_t* __re
     const uint32_t NA = 1u << sp.KA;
     double v;
     if (sp.kind == K_S1) v = log(S[sp.y_off + NA - 1u]);
-    else if (sp.kind == K_S2) v = log(S[sp.y_off + NA - 1u] * S[sp.tabA + (uint64_t)ROW_DM * NA + NA - 1u]);
+    else if (sp.kind == K_S2) v = log(S[sp.y_off + NA - 1u] * side_of(sp, 0, S).special(ROW_DM, NA - 1u));
     else v = log(joint_score(sp, spaces, S));
     logp[sp.patient] = v;
 }
@@ -395,7 +479,7 @@ __global__ void k_direct_acc(const SpaceDev* __restrict__ spaces, const uint32_t
 //   stA[1+a][uA] = sum_uB y[uB,uA] x[uB,uA|a]     stB[1+a][uB] = sum_uA y[uB,uA] x[uB|a,uA]
 // They are all the joint pass has to deliver: every theta / d_p / d_m gradient entry is a
 // contraction of these small tables with the group rate tables (k_finish).
-constexpr int AH = MAXG - 5;
+template <int MB>                                     // MB = 16 (narrow chunks) or MAXG
 __global__ void k_stats_a(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, uint32_t count,
                           double* __restrict__ S)
 {
@@ -412,6 +496,7 @@ __global__ void k_stats_a(const SpaceDev* __restrict__ spaces, const Item* __res
     const uint32_t b0 = it.b * per, b1 = min(NB, b0 + per);
     const double* y = S + sp.y_off;
     const double* x = S + sp.x_off;
+    constexpr int AH = MB - 5;
     double g = 0.0, aL[5] = {0, 0, 0, 0, 0}, aH[AH];
 #pragma unroll
     for (int a = 0; a < AH; ++a) aH[a] = 0.0;
@@ -449,6 +534,7 @@ __global__ void k_stats_a_reduce(const SpaceDev* __restrict__ spaces, const uint
     }
 }
 
+template <int MB>
 __global__ void k_stats_b(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items,
                           double* __restrict__ S)
 {
@@ -461,21 +547,21 @@ __global__ void k_stats_b(const SpaceDev* __restrict__ spaces, const Item* __res
     const uint32_t uB = it.a + w;
     const double* y = S + sp.y_off + ((uint64_t)uB << KA);
     const double* x = S + sp.x_off + ((uint64_t)uB << KA);
-    double g = 0.0, ac[MAXG];
+    double g = 0.0, ac[MB];
 #pragma unroll
-    for (int a = 0; a < MAXG; ++a) ac[a] = 0.0;
+    for (int a = 0; a < MB; ++a) ac[a] = 0.0;
     for (uint32_t uA = lane; uA < NA; uA += 32) {
         const double yv = y[uA];
         g = fma(x[uA], yv, g);
 #pragma unroll
-        for (int a = 0; a < MAXG; ++a)
+        for (int a = 0; a < MB; ++a)
             if (a < KB && !((uB >> a) & 1u)) ac[a] = fma(yv, x[((uint64_t)1 << (a + KA)) + uA], ac[a]);
     }
     double* out = S + sp.stB;
     g = warp_sum(g);
     if (lane == 0) out[uB] = g;
 #pragma unroll
-    for (int a = 0; a < MAXG; ++a)
+    for (int a = 0; a < MB; ++a)
         if (a < KB) {
             const double t = warp_sum(ac[a]);
             if (lane == 0) out[(uint64_t)(1 + a) * NB + uB] = t;
@@ -491,6 +577,7 @@ __global__ void k_stats_b(const SpaceDev* __restrict__ spaces, const Item* __res
 // (likelihood.py:125-201 and vanilla.py:328-393 do this with one shuffle pass per (i, j)).
 // Accumulation is per warp in shared memory, rows are lane-private: no atomics, fixed order.
 constexpr int NACC = 3;                               // effective-parameter spaces: theta, theta_pt/d_p, theta/d_m
+template <int MB>
 __global__ void __launch_bounds__(128)
 k_finish(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, uint32_t count,
          const double* __restrict__ S, double w_type0, double w_other, double* __restrict__ partial)
@@ -511,7 +598,7 @@ k_finish(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, ui
         const int KG = g ? sp.KB : sp.KA;
         const uint32_t NG = 1u << KG;
         const uint8_t* ev = g ? sp.evB : sp.evA;
-        const double* tab = S + (g ? sp.tabB : sp.tabA);
+        const Side sd = side_of(sp, g, S);
         const double* st = S + (g ? sp.stB : sp.stA);
         const double* y = S + sp.y_off;
         const double* x = S + sp.x_off;
@@ -531,14 +618,14 @@ k_finish(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, ui
         int abit = -1;
         for (int b = 0; b < KG; ++b) if (ev[b] == lane) abit = b;
         const double wgt = sp.cls ? w_other : w_type0;
-        double tot = 0.0, ac[MAXG];
+        double tot = 0.0, ac[MB];
 #pragma unroll
-        for (int b = 0; b < MAXG; ++b) ac[b] = 0.0;
+        for (int b = 0; b < MB; ++b) ac[b] = 0.0;
         const uint32_t u1 = min(NG, it.b + FIN_U);
         for (uint32_t u = it.b; u < u1; ++u) {
             double wv = 0.0;
             if (is_row || is_pseudo) {
-                const double R = tab[(uint64_t)lane * NG + u];
+                const double R = is_row ? sd.rate(lane, u) : sd.special(lane, u);
                 double E;
                 if (joint) {
                     const double gg = st[u];
@@ -553,7 +640,7 @@ k_finish(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, ui
             }
             tot += wv;
 #pragma unroll
-            for (int b = 0; b < MAXG; ++b) if (b < KG && ((u >> b) & 1u)) ac[b] += wv;
+            for (int b = 0; b < MB; ++b) if (b < KG && ((u >> b) & 1u)) ac[b] += wv;
         }
         // the seeding edge of the pre-seeding lattice ends in the joint lattice (row n of K_PRE)
         if (sp.kind == K_PRE && lane == n) {
@@ -561,16 +648,16 @@ k_finish(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, ui
             const SpaceDev& j = spaces[sp.joint];
             const double* xj = S + j.x_off;
             for (uint32_t u = it.b; u < u1; ++u) {
-                const double wv = tab[(uint64_t)n * NG + u] * y[u] * xj[((uint64_t)u << j.KA) | u];
+                const double wv = sd.rate(n, u) * y[u] * xj[((uint64_t)u << j.KA) | u];
                 tot += wv;
 #pragma unroll
-                for (int b = 0; b < MAXG; ++b) if (b < KG && ((u >> b) & 1u)) ac[b] += wv;
+                for (int b = 0; b < MB; ++b) if (b < KG && ((u >> b) & 1u)) ac[b] += wv;
             }
         }
         if (is_row || is_pseudo) {
             double* row = G + ((size_t)accid * NR + lane) * NR;
 #pragma unroll
-            for (int b = 0; b < MAXG; ++b) if (b < KG) row[ev[b]] += wgt * ac[b];
+            for (int b = 0; b < MB; ++b) if (b < KG) row[ev[b]] += wgt * ac[b];
             if (is_row) { row[lane] += wgt * tot; if (always_n) row[n] += wgt * tot; }
             else if (pseudo_tot) row[n] += wgt * tot;
         }

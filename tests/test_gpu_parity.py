@@ -108,6 +108,30 @@ def test_big_tier_spaces_against_oracle():
     assert rel_err(g, G) <= TOL
 
 
+def test_wide_groups_against_oracle():
+    """Groups with more than 16 bits use product tables: unpaired patients with 17 events and a lopsided pair."""
+    from metmhn_b200 import Handle
+    from oracle import lattice_direct as ld
+    n = 18
+    rng = np.random.default_rng(18)
+    th = rng.normal(0.0, 0.3, (n + 1, n + 1))
+    th[np.arange(n + 1), np.arange(n + 1)] = rng.normal(-1.0, 0.5, n + 1)
+    dp, dm = rng.normal(0, 0.3, n + 1), rng.normal(0, 0.3, n + 1)
+    rows = np.zeros((4, 2 * n + 3), dtype=np.int8)
+    rows[0, 0:34:2] = 1; rows[0, 2 * n] = 1; rows[0, -2:] = (-99, 1)            # type 1, 17 PT events + seeding
+    rows[1, 1:34:2] = 1; rows[1, 2 * n] = 1; rows[1, -2:] = (-99, 2)            # type 2, 17 MT events
+    rows[2, 0:34:2] = 1; rows[2, 1] = 1; rows[2, 35] = 1; rows[2, 2 * n] = 1; rows[2, -2:] = (0, 3)
+    rows[3, 1:34:2] = 1; rows[3, 0] = 1; rows[3, 34] = 1; rows[3, 2 * n] = 1; rows[3, -2:] = (2, 3)
+    params = np.concatenate([th.ravel(), dp, dm])
+    for r in range(rows.shape[0]):
+        h = Handle(rows[r:r + 1])
+        s, g = h.eval_weighted(params, 1.0, 1.0)
+        h.close()
+        out = ld.patient_value_grad(th, dp, dm, rows[r])
+        assert abs(s - out[1]) <= TOL * abs(out[1]), r
+        assert rel_err(g, np.concatenate([out[2].ravel(), out[3], out[4]])) <= TOL, r
+
+
 def test_chunking_and_repeatability():
     """Small scratch chunks give the same numbers; repeated evaluations are bit-identical."""
     from metmhn_b200 import Handle
