@@ -54,6 +54,9 @@ typedef struct mmh_stats_t {
     double  last_ms;          /* device time of the last evaluation (CUDA events) */
     double  scratch_bytes;    /* device scratch allocated */
     int64_t k_hist[4][64];    /* [type][k] histogram of restricted sizes */
+    double  class_ms[8];      /* profile mode: device ms by kernel class of the last evaluation:
+                                 0 table setup, 1 forward solves, 2 adjoint solves, 3 marginal statistics,
+                                 4 gradient contraction, 5 other */
 } mmh_stats_t;
 
 /* Copy + preprocess the dataset (parse rows, canonical bit layout, bucket by lattice size,
@@ -77,6 +80,17 @@ int mmh_value(mmh_handle* h, const double* params, double perc_met, double* scor
  * want_grad = 0 writes only out[0]. */
 int mmh_eval_weighted(mmh_handle* h, const double* params, double w_type0, double w_other,
                       int want_grad, double* out_host, double* out_dev);
+
+/* Asynchronous variant for device-resident callers: d_params and d_out are DEVICE pointers on the
+ * handle's device (d_out: 1 + (n+1)(n+3) doubles).  Work is queued on the handle's stream; call
+ * mmh_sync() before reading d_out from another stream or the host. */
+int mmh_eval_device(mmh_handle* h, const double* d_params, double w_type0, double w_other,
+                    int want_grad, double* d_out);
+int mmh_sync(mmh_handle* h);
+
+/* Profile mode: time every kernel class of an evaluation with CUDA events on the launching stream
+ * (mmh_stats_t.class_ms).  Adds a synchronisation per evaluation; off by default. */
+int mmh_set_profile(mmh_handle* h, int on);
 
 /* Per-row log-likelihoods of the last evaluation's parameters (test hook).  Rows with an
  * unknown type get 0. */

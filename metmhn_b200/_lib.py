@@ -17,7 +17,8 @@ LIB_PATH = os.path.join(_HERE, "libmetmhn_b200.so")
 MMH_OK, MMH_EINVAL, MMH_ECUDA, MMH_ENOMEM, MMH_ETOOLARGE = 0, -1, -2, -3, -4
 MAX_MUT = 28
 
-EXPORTS = ("mmh_create", "mmh_value_grad", "mmh_value", "mmh_eval_weighted", "mmh_per_patient",
+EXPORTS = ("mmh_create", "mmh_value_grad", "mmh_value", "mmh_eval_weighted", "mmh_eval_device", "mmh_sync",
+           "mmh_set_profile", "mmh_per_patient",
            "mmh_stats", "mmh_destroy", "mmh_last_error", "mmh_measure_fp64_tflops")
 
 
@@ -25,7 +26,7 @@ class Stats(C.Structure):
     _fields_ = [("n_dat", C.c_int64), ("n_em", C.c_int64), ("n_spaces", C.c_int64), ("n_chunks", C.c_int64),
                 ("n_launches", C.c_int64), ("states_value_grad", C.c_double), ("alg_bytes", C.c_double),
                 ("alg_flops", C.c_double), ("exec_fma", C.c_double), ("last_ms", C.c_double),
-                ("scratch_bytes", C.c_double), ("k_hist", (C.c_int64 * 64) * 4)]
+                ("scratch_bytes", C.c_double), ("k_hist", (C.c_int64 * 64) * 4), ("class_ms", C.c_double * 8)]
 
 
 class MetMHNError(RuntimeError):
@@ -50,6 +51,9 @@ def lib():
     L.mmh_value_grad.argtypes = [C.c_void_p, dp, C.c_double, dp, dp]
     L.mmh_value.argtypes = [C.c_void_p, dp, C.c_double, dp]
     L.mmh_eval_weighted.argtypes = [C.c_void_p, dp, C.c_double, C.c_double, C.c_int, dp, C.c_void_p]
+    L.mmh_eval_device.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p]
+    L.mmh_sync.argtypes = [C.c_void_p]
+    L.mmh_set_profile.argtypes = [C.c_void_p, C.c_int]
     L.mmh_per_patient.argtypes = [C.c_void_p, dp, dp]
     L.mmh_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     L.mmh_destroy.argtypes = [C.c_void_p]
@@ -117,6 +121,17 @@ class Handle:
             return None
         return (out[0], out[1:]) if want_grad else (out[0], None)
 
+    def eval_device(self, d_params_ptr, w_type0, w_other, d_out_ptr, want_grad=True):
+        """Queue one evaluation with device-resident parameters / result (raw device pointers)."""
+        check(lib().mmh_eval_device(self._h, C.c_void_p(d_params_ptr), float(w_type0), float(w_other),
+                                    int(bool(want_grad)), C.c_void_p(d_out_ptr)))
+
+    def sync(self):
+        check(lib().mmh_sync(self._h))
+
+    def set_profile(self, on):
+        check(lib().mmh_set_profile(self._h, int(bool(on))))
+
     def per_patient(self, params):
         p = self._params(params)
         out = np.zeros(max(self.n_dat, 1))
@@ -126,7 +141,8 @@ class Handle:
     def stats(self):
         s = Stats()
         check(lib().mmh_stats(self._h, C.byref(s)))
-        d = {k: getattr(s, k) for k, _ in Stats._fields_ if k != "k_hist"}
+        d = {k: getattr(s, k) for k, _ in Stats._fields_ if k not in ("k_hist", "class_ms")}
+        d["class_ms"] = dict(zip(("setup", "solve_fwd", "solve_adj", "stats", "finish", "other"), list(s.class_ms)[:6]))
         d["k_hist"] = {t: {k: int(s.k_hist[t][k]) for k in range(64) if s.k_hist[t][k]} for t in range(4)}
         return d
 

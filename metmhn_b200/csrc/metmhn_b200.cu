@@ -60,6 +60,8 @@ struct mmh_handle {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int fin_ctas = 0;
+    int profile = 0;
+    std::vector<cudaEvent_t> evpool;
     uint32_t max_joints = 0;
     mmh_stats_t st{};
 };
@@ -378,15 +380,24 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
     return MMH_OK;
 }
 
-static int run_eval(mmh_handle* h, const double* params, double w0, double w1, int want_grad)
+// Launch one evaluation on the handle's stream (asynchronous).  d_params is a DEVICE pointer.
+static int run_eval(mmh_handle* h, const double* d_params, double w0, double w1, int want_grad)
 {
     CK(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
-    const size_t npar = (size_t)h->n_tot * (h->n_tot + 2);
     int64_t launches = 0;
-    CK(cudaMemcpyAsync(h->d_params, params, npar * sizeof(double), cudaMemcpyHostToDevice, st));
+    // optional per-class timing (profile mode): CUDA events around every launch group
+    size_t evn = 0;
+    std::vector<int> evcls;
+    auto tick = [&](int cls) {
+        if (!h->profile) return;
+        if (evn >= h->evpool.size()) { cudaEvent_t e; cudaEventCreate(&e); h->evpool.push_back(e); }
+        cudaEventRecord(h->evpool[evn++], st);
+        evcls.push_back(cls);
+    };
     CK(cudaEventRecord(h->ev0, st));
-    k_prep<<<1, 1024, 0, st>>>(h->d_params, h->n_tot, h->d_par); ++launches;
+    tick(5);
+    k_prep<<<1, 1024, 0, st>>>(d_params, h->n_tot, h->d_par); ++launches;
     if (want_grad) {
         CK(cudaMemsetAsync(h->d_partial, 0, (size_t)h->fin_ctas * NACC * NR * NR * sizeof(double), st));
         CK(cudaMemsetAsync(h->d_diracc, 0, 2 * NR * sizeof(double), st));
@@ -411,25 +422,32 @@ static int run_eval(mmh_handle* h, const double* params, double w0, double w1, i
                 ++launches;
             }
         };
+        tick(0);
         k_setup<<<ck.setup.cnt, 128, 0, st>>>(sp, h->d_items + ck.setup.off, h->d_par, S); ++launches;
         if (ck.setup_wide.cnt) { k_setup_wide<<<ck.setup_wide.cnt, 1024, 0, st>>>(sp, h->d_items + ck.setup_wide.off, h->d_par, S); ++launches; }
+        tick(1);
         small(ck.pre, false);
         small(ck.main_small, false);
         big(ck.main_lv, false);
         small(ck.sec_small, false);
         big(ck.sec_lv, false);
+        tick(5);
         if (ck.logp.cnt) { k_logp<<<(ck.logp.cnt + 127) / 128, 128, 0, st>>>(sp, h->d_lists + ck.logp.off, ck.logp.cnt, S, h->d_logp); ++launches; }
         if (!want_grad) continue;
+        tick(2);
         small(ck.sec_small, true);
         big(ck.sec_lv, true);
+        tick(5);
         if (ck.joints.cnt) {
             k_direct<<<(ck.joints.cnt + 7) / 8, 256, 0, st>>>(sp, h->d_lists + ck.joints.off, ck.joints.cnt, S, h->d_tdir);
             k_direct_acc<<<dim3(h->n_tot, 2), 256, 0, st>>>(sp, h->d_lists + ck.joints.off, ck.joints.cnt, h->d_tdir, w1, h->d_diracc);
             launches += 2;
         }
+        tick(2);
         small(ck.main_small, true);
         big(ck.main_lv, true);
         small(ck.pre, true);
+        tick(3);
         if (ck.st_a.cnt) {
             if (ck.wide) k_stats_a<MAXG><<<(ck.st_a.cnt + 7) / 8, 256, 0, st>>>(sp, h->d_items + ck.st_a.off, ck.st_a.cnt, S);
             else         k_stats_a<MAXT><<<(ck.st_a.cnt + 7) / 8, 256, 0, st>>>(sp, h->d_items + ck.st_a.off, ck.st_a.cnt, S);
@@ -438,17 +456,29 @@ static int run_eval(mmh_handle* h, const double* params, double w0, double w1, i
             else         k_stats_b<MAXT><<<ck.st_b.cnt, 256, 0, st>>>(sp, h->d_items + ck.st_b.off, S);
             launches += 3;
         }
+        tick(4);
         const size_t fin_smem = 4 * NACC * NR * NR * sizeof(double);
         if (ck.wide) k_finish<MAXG><<<h->fin_ctas, 128, fin_smem, st>>>(sp, h->d_items + ck.fin.off, ck.fin.cnt, S, w0, w1, h->d_partial);
         else         k_finish<MAXT><<<h->fin_ctas, 128, fin_smem, st>>>(sp, h->d_items + ck.fin.off, ck.fin.cnt, S, w0, w1, h->d_partial);
         ++launches;
     }
+    tick(5);
     k_final<<<1, 1024, 0, st>>>(h->d_partial, h->fin_ctas, h->d_diracc, h->d_logp, h->d_cls, h->n_dat, h->d_cnt, w0, w1,
                                 h->n_tot, want_grad, h->d_out);
     ++launches;
+    tick(-1);
     CK(cudaEventRecord(h->ev1, st));
     CK(cudaGetLastError());
     h->st.n_launches = launches;
+    if (h->profile) {
+        CK(cudaStreamSynchronize(st));
+        for (int c = 0; c < 8; ++c) h->st.class_ms[c] = 0.0;
+        for (size_t i = 0; i + 1 < evn; ++i) {
+            float ms = 0.f;
+            if (evcls[i] >= 0 && cudaEventElapsedTime(&ms, h->evpool[i], h->evpool[i + 1]) == cudaSuccess)
+                h->st.class_ms[evcls[i]] += ms;
+        }
+    }
     return MMH_OK;
 }
 
@@ -466,7 +496,9 @@ extern "C" int mmh_eval_weighted(mmh_handle* h, const double* params, double w_t
                                  int want_grad, double* out_host, double* out_dev)
 {
     if (!h || !params) return fail(MMH_EINVAL, "mmh_eval_weighted: null argument");
-    int rc = run_eval(h, params, w_type0, w_other, want_grad);
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->d_params, params, (size_t)h->n_tot * (h->n_tot + 2) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    int rc = run_eval(h, h->d_params, w_type0, w_other, want_grad);
     if (rc != MMH_OK) return rc;
     const size_t len = want_grad ? (size_t)h->n_tot * (h->n_tot + 2) + 1 : 1;
     if (out_dev) CK(cudaMemcpyAsync(out_dev, h->d_out, len * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
@@ -475,6 +507,34 @@ extern "C" int mmh_eval_weighted(mmh_handle* h, const double* params, double w_t
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->st.last_ms = ms;
     if (out_host) std::memcpy(out_host, h->h_out, len * sizeof(double));
+    return MMH_OK;
+}
+
+extern "C" int mmh_eval_device(mmh_handle* h, const double* d_params, double w_type0, double w_other,
+                               int want_grad, double* d_out)
+{
+    if (!h || !d_params || !d_out) return fail(MMH_EINVAL, "mmh_eval_device: null argument");
+    int rc = run_eval(h, d_params, w_type0, w_other, want_grad);
+    if (rc != MMH_OK) return rc;
+    const size_t len = want_grad ? (size_t)h->n_tot * (h->n_tot + 2) + 1 : 1;
+    CK(cudaMemcpyAsync(d_out, h->d_out, len * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    return MMH_OK;
+}
+
+extern "C" int mmh_sync(mmh_handle* h)
+{
+    if (!h) return fail(MMH_EINVAL, "mmh_sync: null argument");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->st.last_ms = ms;
+    return MMH_OK;
+}
+
+extern "C" int mmh_set_profile(mmh_handle* h, int on)
+{
+    if (!h) return fail(MMH_EINVAL, "mmh_set_profile: null argument");
+    h->profile = on ? 1 : 0;
     return MMH_OK;
 }
 
@@ -528,6 +588,7 @@ extern "C" void mmh_destroy(mmh_handle* h)
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    for (cudaEvent_t e : h->evpool) cudaEventDestroy(e);
     delete h;
 }
 
