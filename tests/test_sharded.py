@@ -1,0 +1,88 @@
+"""CPU tests of the multi-GPU host logic: cost-model partition and the world-size-2 reduction (gloo).
+The shard evaluator is injected (CPU oracle) so that the plumbing is exercised without a GPU."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from metmhn_b200.sharded import ShardedEvaluator, class_weights, partition, patient_cost
+from metmhn_b200.simulate import syn_v1
+
+
+def test_partition_is_balanced_and_complete():
+    d = syn_v1(12, 2000, 12)
+    dat = d["dat"]
+    for world in (2, 4, 8):
+        a = partition(dat, world)
+        assert a.shape[0] == dat.shape[0] and set(np.unique(a)) == set(range(world))
+        cost = patient_cost(dat)
+        loads = np.array([cost[a == r].sum() for r in range(world)])
+        # LPT guarantee: max load <= mean + largest item
+        assert loads.max() <= loads.mean() + cost.max() + 1e-9
+    assert np.array_equal(partition(dat, 4), partition(dat, 4))      # deterministic
+
+
+def test_class_weights_match_reference_formula():
+    w0, w1 = class_weights(100, 80, 0.65)
+    w = 0.65 * 20 / (0.35 * 80)
+    assert abs(w1 / w0 - w) < 1e-15 and abs(1 / w0 - (w * 80 + 20)) < 1e-12
+    assert class_weights(10, 0, 0.3) == (0.1, 0.1)                    # n_em * n_nm == 0 -> w = 1
+
+
+def _oracle_local_eval(shard):
+    from oracle import lattice_direct as ld
+
+    def f(params, w0, w1, want_grad):
+        n = (shard.shape[1] - 3) // 2
+        n_tot = n + 1
+        th, dp, dm = params[:n_tot ** 2].reshape(n_tot, n_tot), params[n_tot ** 2:n_tot ** 2 + n_tot], params[n_tot ** 2 + n_tot:]
+        out = np.zeros(1 + n_tot * (n_tot + 2))
+        for r in shard:
+            o = ld.patient_value_grad(th, dp, dm, r)
+            if o is None:
+                continue
+            w = w0 if o[0] else w1
+            out[0] += w * o[1]
+            out[1:] += w * np.concatenate([o[2].ravel(), o[3], o[4]])
+        return out if want_grad else out[:1]
+    return f
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d = syn_v1(5, 40, 55)
+    ev = ShardedEvaluator(d["dat"], rank=rank, world=world, local_eval=lambda *a: None)
+    ev.local_eval = _oracle_local_eval(ev.shard)
+    s, g = ev.value_grad(d["eval_point"], 0.65)
+    v = ev.value(d["eval_point"], 0.65)
+    q.put((rank, s, g, v, ev.shard.shape[0]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_matches_single_process():
+    import torch.multiprocessing as mp
+    from oracle import lattice_direct as ld
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    d = syn_v1(5, 40, 55)
+    ep = d["eval_point"]
+    s0, g0, a0, b0 = ld.score_and_grad(ep[:36].reshape(6, 6), ep[36:42], ep[42:], d["dat"], 0.65)
+    ref = np.concatenate([g0.ravel(), a0, b0])
+    assert res[0][4] + res[1][4] == 40
+    for _, s, g, v, _ in res:
+        assert abs(s - s0) <= 1e-12 * abs(s0) and abs(v - s0) <= 1e-12 * abs(s0)
+        assert np.abs(g - ref).max() <= 1e-12 * np.abs(ref).max()
