@@ -31,7 +31,7 @@ struct Range { uint64_t off = 0; uint32_t cnt = 0; };
 struct ChunkPlan {
     uint64_t space0 = 0;
     uint32_t nspaces = 0;
-    Range setup, setup_wide, pre, main_small, sec_small, logp, joints, st_a, st_b, fin;
+    Range setup, setup_wide, pre, main_small, sec_small, logp, joints, st_a, st_ar, st_b, fin;
     bool wide = false;                           // some group has more than MAXT bits
     std::vector<Range> main_lv, sec_lv;          // big-tier segments per popcount level
     uint64_t scratch = 0;                        // doubles
@@ -70,10 +70,14 @@ static uint64_t space_scratch(SpaceDev& s, uint64_t off)
 {
     const uint64_t NA = 1ull << s.KA, NB = 1ull << s.KB, N = NA * NB;
     auto take = [&](uint64_t len) { uint64_t o = off; off += (len + 3) & ~3ull; return o; };
+    // A joint side's table (NR x 2^KG) is small next to the 2^(KA+KB) vectors; a single-group space's full table
+    // would be NR times its vectors, so those switch to the product form early.
+    const int max_full = (s.kind == K_JOINT) ? MAXT : 8;
+    const bool has_diag_tables = (s.kind == K_PRE || s.kind == K_JOINT || s.kind == K_S2);
     auto table = [&](int KG, uint8_t& split) {
-        if (KG <= MAXT) { split = 0; return take((uint64_t)NR << KG); }
-        split = (uint8_t)((KG + 1) / 2);             // rate(i,u) = T1[i][u_lo] * T2[i][u_hi] + three full vectors
-        return take(((uint64_t)NR << split) + ((uint64_t)NR << (KG - split)) + (3ull << KG));
+        if (KG <= max_full) { split = 0; return take((uint64_t)NR << KG); }
+        split = (uint8_t)((KG + 1) / 2);             // rate(i,u) = T1[i][u_lo] * T2[i][u_hi] + full special-row vectors
+        return take(((uint64_t)NR << split) + ((uint64_t)NR << (KG - split)) + ((has_diag_tables ? 3ull : 1ull) << KG));
     };
     s.splitA = s.splitB = 0;
     s.tabA = table(s.KA, s.splitA);
@@ -283,13 +287,14 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
         ck.joints = list_of([&](const SpaceDev& s) { return s.kind == K_JOINT; });
         h->max_joints = std::max(h->max_joints, ck.joints.cnt);
         ck.setup.off = items.size();
+        auto setup_items = [&](uint32_t i, uint32_t g, int KG, int K1) {
+            auto blocks = [&](uint32_t part, int bits) { for (uint32_t u = 0; u < (1u << bits); u += 256) items.push_back({i, g | (part << 1), u}); };
+            if (!K1) blocks(0, KG); else { blocks(0, K1); blocks(1, KG - K1); }
+            if (KG > MAXT) ck.wide = true;
+        };
         for (uint32_t i = 0; i < ck.nspaces; ++i) {
-            items.push_back({i, 0u, 0u});
-            if (sp[i].splitA) { items.push_back({i, 0u, 1u}); ck.wide = true; }
-            if (sp[i].kind == K_JOINT) {
-                items.push_back({i, 1u, 0u});
-                if (sp[i].splitB) { items.push_back({i, 1u, 1u}); ck.wide = true; }
-            }
+            setup_items(i, 0, sp[i].KA, sp[i].splitA);
+            if (sp[i].kind == K_JOINT) setup_items(i, 1, sp[i].KB, sp[i].splitB);
         }
         ck.setup.cnt = (uint32_t)(items.size() - ck.setup.off);
         ck.setup_wide.off = items.size();
@@ -327,6 +332,13 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
                     for (uint32_t b = 0; b < nblk; ++b) items.push_back({i, b, sl});
             }
         ck.st_a.cnt = (uint32_t)(items.size() - ck.st_a.off);
+        ck.st_ar.off = items.size();
+        for (uint32_t i = 0; i < ck.nspaces; ++i)
+            if (sp[i].kind == K_JOINT) {
+                const uint64_t len = (uint64_t)(sp[i].KA + 1) << sp[i].KA;
+                for (uint64_t t = 0; t < len; t += 1024) items.push_back({i, 0u, (uint32_t)(t / 1024)});
+            }
+        ck.st_ar.cnt = (uint32_t)(items.size() - ck.st_ar.off);
         ck.st_b.off = items.size();
         for (uint32_t i = 0; i < ck.nspaces; ++i)
             if (sp[i].kind == K_JOINT)
@@ -423,7 +435,7 @@ static int run_eval(mmh_handle* h, const double* d_params, double w0, double w1,
             }
         };
         tick(0);
-        k_setup<<<ck.setup.cnt, 128, 0, st>>>(sp, h->d_items + ck.setup.off, h->d_par, S); ++launches;
+        k_setup<<<ck.setup.cnt, 256, 0, st>>>(sp, h->d_items + ck.setup.off, h->d_par, S); ++launches;
         if (ck.setup_wide.cnt) { k_setup_wide<<<ck.setup_wide.cnt, 1024, 0, st>>>(sp, h->d_items + ck.setup_wide.off, h->d_par, S); ++launches; }
         tick(1);
         small(ck.pre, false);
@@ -439,7 +451,7 @@ static int run_eval(mmh_handle* h, const double* d_params, double w0, double w1,
         big(ck.sec_lv, true);
         tick(5);
         if (ck.joints.cnt) {
-            k_direct<<<(ck.joints.cnt + 7) / 8, 256, 0, st>>>(sp, h->d_lists + ck.joints.off, ck.joints.cnt, S, h->d_tdir);
+            k_direct<<<(ck.joints.cnt + 255) / 256, 256, 0, st>>>(sp, h->d_lists + ck.joints.off, ck.joints.cnt, S, h->d_tdir);
             k_direct_acc<<<dim3(h->n_tot, 2), 256, 0, st>>>(sp, h->d_lists + ck.joints.off, ck.joints.cnt, h->d_tdir, w1, h->d_diracc);
             launches += 2;
         }
@@ -451,7 +463,7 @@ static int run_eval(mmh_handle* h, const double* d_params, double w0, double w1,
         if (ck.st_a.cnt) {
             if (ck.wide) k_stats_a<MAXG><<<(ck.st_a.cnt + 7) / 8, 256, 0, st>>>(sp, h->d_items + ck.st_a.off, ck.st_a.cnt, S);
             else         k_stats_a<MAXT><<<(ck.st_a.cnt + 7) / 8, 256, 0, st>>>(sp, h->d_items + ck.st_a.off, ck.st_a.cnt, S);
-            k_stats_a_reduce<<<ck.joints.cnt, 256, 0, st>>>(sp, h->d_lists + ck.joints.off, S);
+            k_stats_a_reduce<<<ck.st_ar.cnt, 1024, 0, st>>>(sp, h->d_items + ck.st_ar.off, S);
             if (ck.wide) k_stats_b<MAXG><<<ck.st_b.cnt, 256, 0, st>>>(sp, h->d_items + ck.st_b.off, S);
             else         k_stats_b<MAXT><<<ck.st_b.cnt, 256, 0, st>>>(sp, h->d_items + ck.st_b.off, S);
             launches += 3;

@@ -158,9 +158,9 @@ __device__ __forceinline__ void diag_rates(int dg, int KG, const uint8_t* sev, i
 __global__ void k_setup(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items,
                         const EvalPar* __restrict__ P, double* __restrict__ S)
 {
-    const Item it = items[blockIdx.x];
+    const Item it = items[blockIdx.x];                      // a = group | part << 1, b = first entry of this block
     const SpaceDev& sp = spaces[it.space];
-    const int g = it.a, part = it.b;
+    const int g = it.a & 1, part = it.a >> 1;
     const int KG = g ? sp.KB : sp.KA;
     const int K1 = g ? sp.splitB : sp.splitA;
     const int b0 = part ? K1 : 0;                           // first bit of this table
@@ -171,28 +171,28 @@ __global__ void k_setup(const SpaceDev* __restrict__ spaces, const Item* __restr
     const int n = sp.n_tot - 1;
     const SetupSel sel = setup_sel(sp, g);
     __shared__ uint8_t sev[MAXG];
-    if (threadIdx.x < MAXG) sev[threadIdx.x] = threadIdx.x < KT ? ev[threadIdx.x] : 255;
+    if (threadIdx.x < MAXG) sev[threadIdx.x] = (int)threadIdx.x < KT ? ev[threadIdx.x] : 255;
     __syncthreads();
-    for (uint32_t u = threadIdx.x; u < NT; u += blockDim.x) {
-        double dsum = 0.0;
-        for (int i = 0; i < sel.nrows; ++i) {
-            double r = part ? 1.0 : P->base[sel.bid][i];
-            bool in_u = false;
-            for (int b = 0; b < KT; ++b)
-                if ((u >> b) & 1u) {
-                    const int e = sev[b];
-                    if (e == i) in_u = true; else r *= P->W[sel.wid][i][e];
-                }
-            tab[(uint64_t)i * NT + u] = r;
-            if (!in_u) dsum += r;
-        }
-        if (K1 == 0) {
-            double d, vdp, vdm;
-            diag_rates(sel.dg, KG, sev, n, P, u, d, vdp, vdm);
-            tab[(uint64_t)ROW_D * NT + u]  = d + dsum;
-            tab[(uint64_t)ROW_DP * NT + u] = vdp;
-            tab[(uint64_t)ROW_DM * NT + u] = vdm;
-        }
+    const uint32_t u = it.b + threadIdx.x;
+    if (u >= NT) return;
+    double dsum = 0.0;
+    for (int i = 0; i < sel.nrows; ++i) {
+        double r = part ? 1.0 : P->base[sel.bid][i];
+        bool in_u = false;
+        for (int b = 0; b < KT; ++b)
+            if ((u >> b) & 1u) {
+                const int e = sev[b];
+                if (e == i) in_u = true; else r *= P->W[sel.wid][i][e];
+            }
+        tab[(uint64_t)i * NT + u] = r;
+        if (!in_u) dsum += r;
+    }
+    if (K1 == 0) {
+        double d, vdp, vdm;
+        diag_rates(sel.dg, KG, sev, n, P, u, d, vdp, vdm);
+        tab[(uint64_t)ROW_D * NT + u]  = d + dsum;
+        tab[(uint64_t)ROW_DP * NT + u] = vdp;
+        tab[(uint64_t)ROW_DM * NT + u] = vdm;
     }
 }
 
@@ -230,8 +230,10 @@ __global__ void k_setup_wide(const SpaceDev* __restrict__ spaces, const Item* __
     double d, vdp, vdm;
     diag_rates(sel.dg, KG, sev, n, P, u, d, vdp, vdm);
     vec[u] = d + dsum;
-    vec[(uint64_t)NG + u] = vdp;
-    vec[2ull * NG + u] = vdm;
+    if (sel.dg != 0) {                                      // kinds without diagnosis tables keep only the diagonal
+        vec[(uint64_t)NG + u] = vdp;
+        vec[2ull * NG + u] = vdm;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -430,26 +432,21 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-// direct dependence of the second-phase start vector on the diagnosis effects
-// (likelihood.py:574-576, 617-619): T = x2 . v, one warp per joint space.
+// direct dependence of the second-phase start vector v = c * (slice of the joint y) on the diagnosis effects
+// (likelihood.py:574-576, 617-619):  T = x2 . v  with  A2 p2 = v  and  A2^T x2 = e_last / score,
+// hence  T = e_last^T p2 / score = score_side / score.  One thread per joint space.
 __global__ void k_direct(const SpaceDev* __restrict__ spaces, const uint32_t* __restrict__ list, uint32_t count,
                          const double* __restrict__ S, double* __restrict__ tdir)
 {
-    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (w >= count) return;
-    const SpaceDev& j = spaces[list[w]];
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const SpaceDev& j = spaces[list[t]];
+    const double sc = joint_score(j, spaces, S);
     double tp = 0.0, tm = 0.0;
-    if (j.has_pf) {
-        const SpaceDev& q = spaces[j.pf];
-        for (uint32_t u = lane; u < (1u << q.KA); u += 32) tp += S[q.x_off + u] * rhs_fwd(q, spaces, S, u);
-    }
-    if (j.has_mf) {
-        const SpaceDev& q = spaces[j.mf];
-        for (uint32_t u = lane; u < (1u << q.KA); u += 32) tm += S[q.x_off + u] * rhs_fwd(q, spaces, S, u);
-    }
-    tp = warp_sum(tp); tm = warp_sum(tm);
-    if (lane == 0) { tdir[2 * w] = tp; tdir[2 * w + 1] = tm; }
+    if (j.has_pf) { const SpaceDev& q = spaces[j.pf]; tp = S[q.y_off + ((1u << q.KA) - 1u)] / sc; }
+    if (j.has_mf) { const SpaceDev& q = spaces[j.mf]; tm = S[q.y_off + ((1u << q.KA) - 1u)] / sc; }
+    tdir[2 * t] = tp;
+    tdir[2 * t + 1] = tm;
 }
 
 // diracc[side][e] += sum over the chunk's joint spaces of wgt * T_side * [e in mask_side or e == n]
@@ -522,16 +519,17 @@ __global__ void k_stats_a(const SpaceDev* __restrict__ spaces, const Item* __res
     for (int a = 0; a < AH; ++a) if (a + 5 < KA) out[(uint64_t)(6 + a) * NA + uA] = aH[a];
 }
 
-__global__ void k_stats_a_reduce(const SpaceDev* __restrict__ spaces, const uint32_t* __restrict__ list,
+__global__ void k_stats_a_reduce(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items,
                                  double* __restrict__ S)
 {
-    const SpaceDev& sp = spaces[list[blockIdx.x]];   // one CTA per joint space
+    const Item it = items[blockIdx.x];               // b = first element of a 1024-element block (in units of 1024)
+    const SpaceDev& sp = spaces[it.space];
     const uint64_t len = (uint64_t)(sp.KA + 1) << sp.KA;
-    for (uint64_t t = threadIdx.x; t < len; t += blockDim.x) {
-        double s = 0.0;
-        for (uint32_t k = 0; k < sp.slices; ++k) s += S[sp.stP + k * len + t];
-        S[sp.stA + t] = s;
-    }
+    const uint64_t t = (uint64_t)it.b * 1024u + threadIdx.x;
+    if (t >= len) return;
+    double s = 0.0;
+    for (uint32_t k = 0; k < sp.slices; ++k) s += S[sp.stP + k * len + t];
+    S[sp.stA + t] = s;
 }
 
 template <int MB>
@@ -614,7 +612,8 @@ k_finish(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, ui
             default:      nrows = n_tot; accid = 0; break;
         }
         const bool is_row = lane < nrows;
-        const bool is_pseudo = (lane == ROW_DP || lane == ROW_DM);
+        const bool is_pseudo = (lane == ROW_DP || lane == ROW_DM) &&
+                               (sp.kind == K_PRE || sp.kind == K_JOINT || sp.kind == K_S2);
         int abit = -1;
         for (int b = 0; b < KG; ++b) if (ev[b] == lane) abit = b;
         const double wgt = sp.cls ? w_other : w_type0;
