@@ -31,7 +31,7 @@ struct Range { uint64_t off = 0; uint32_t cnt = 0; };
 struct ChunkPlan {
     uint64_t space0 = 0;
     uint32_t nspaces = 0;
-    Range setup, setup_wide, pre, main_small, sec_small, logp, joints, st_a, st_ar, st_b, fin;
+    Range setup, setup_wide, pre, main_small, sec_small, logp, joints, st_a, st_ar, st_b, pf_lo, pf_hi, fin;
     bool wide = false;                           // some group has more than MAXT bits
     std::vector<Range> main_lv, sec_lv;          // big-tier segments per popcount level
     uint64_t scratch = 0;                        // doubles
@@ -91,6 +91,11 @@ static uint64_t space_scratch(SpaceDev& s, uint64_t off)
         s.stA = take((s.KA + 1) * NA);
         s.stB = take((s.KB + 1) * NB);
         s.stP = take((uint64_t)s.slices * (s.KA + 1) * NA);
+    } else if (s.kind != K_PRE && s.splitA) {
+        // product-form gradient: weighted marginals over the low / high part (k_pfin_lo / k_pfin_hi)
+        const uint64_t N1 = 1ull << s.splitA, N2 = 1ull << (s.KA - s.splitA);
+        s.slices = (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(1, N2 / 64));
+        s.stP = take((uint64_t)s.slices * (NR + s.KA) * N1 + (uint64_t)(NR + s.KA) * N2);
     }
     return off;
 }
@@ -256,6 +261,7 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
             for (SpaceDev s : pp.sp) {
                 s.y_off += used; s.x_off += used; s.tabA += used;
                 if (s.kind == K_JOINT) { s.tabB += used; s.stA += used; s.stB += used; s.stP += used; }
+                else if (s.stP) s.stP += used;                  // product-form single-tumour spaces
                 if (s.joint >= 0) s.joint += base_idx;
                 if (s.pre >= 0) s.pre += base_idx;
                 if (s.pf >= 0) s.pf += base_idx;
@@ -344,8 +350,29 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
             if (sp[i].kind == K_JOINT)
                 for (uint32_t u = 0; u < (1u << sp[i].KB); u += 8) items.push_back({i, u, std::min<uint32_t>(8u, (1u << sp[i].KB) - u)});
         ck.st_b.cnt = (uint32_t)(items.size() - ck.st_b.off);
+        auto is_prod = [](const SpaceDev& s) { return s.kind != K_JOINT && s.kind != K_PRE && s.splitA; };
+        ck.pf_lo.off = items.size();
+        for (uint32_t i = 0; i < ck.nspaces; ++i)
+            if (is_prod(sp[i])) {
+                const uint32_t nch = std::max<uint32_t>(1u, (1u << sp[i].splitA) >> 5);
+                for (uint32_t sl = 0; sl < sp[i].slices; ++sl)
+                    for (uint32_t c = 0; c < nch; ++c) items.push_back({i, c, sl});
+            }
+        ck.pf_lo.cnt = (uint32_t)(items.size() - ck.pf_lo.off);
+        ck.pf_hi.off = items.size();
+        for (uint32_t i = 0; i < ck.nspaces; ++i)
+            if (is_prod(sp[i])) {
+                const uint32_t N2 = 1u << (sp[i].KA - sp[i].splitA);
+                for (uint32_t u = 0; u < N2; u += 8) items.push_back({i, u, std::min<uint32_t>(8u, N2 - u)});
+            }
+        ck.pf_hi.cnt = (uint32_t)(items.size() - ck.pf_hi.off);
         ck.fin.off = items.size();
         for (uint32_t i = 0; i < ck.nspaces; ++i) {
+            if (is_prod(sp[i])) {
+                for (uint32_t u = 0; u < (1u << sp[i].splitA); u += FIN_U) items.push_back({i, 2u, u});
+                for (uint32_t u = 0; u < (1u << (sp[i].KA - sp[i].splitA)); u += FIN_U) items.push_back({i, 3u, u});
+                continue;
+            }
             for (uint32_t u = 0; u < (1u << sp[i].KA); u += FIN_U) items.push_back({i, 0u, u});
             if (sp[i].kind == K_JOINT)
                 for (uint32_t u = 0; u < (1u << sp[i].KB); u += FIN_U) items.push_back({i, 1u, u});
@@ -469,6 +496,16 @@ static int run_eval(mmh_handle* h, const double* d_params, double w0, double w1,
             launches += 3;
         }
         tick(4);
+        if (ck.pf_lo.cnt) {
+            if (ck.wide) {
+                k_pfin_lo<MAXG><<<(ck.pf_lo.cnt + 7) / 8, 256, 0, st>>>(sp, h->d_items + ck.pf_lo.off, ck.pf_lo.cnt, S);
+                k_pfin_hi<MAXG><<<ck.pf_hi.cnt, 256, 0, st>>>(sp, h->d_items + ck.pf_hi.off, S);
+            } else {
+                k_pfin_lo<MAXT><<<(ck.pf_lo.cnt + 7) / 8, 256, 0, st>>>(sp, h->d_items + ck.pf_lo.off, ck.pf_lo.cnt, S);
+                k_pfin_hi<MAXT><<<ck.pf_hi.cnt, 256, 0, st>>>(sp, h->d_items + ck.pf_hi.off, S);
+            }
+            launches += 2;
+        }
         const size_t fin_smem = 4 * NACC * NR * NR * sizeof(double);
         if (ck.wide) k_finish<MAXG><<<h->fin_ctas, 128, fin_smem, st>>>(sp, h->d_items + ck.fin.off, ck.fin.cnt, S, w0, w1, h->d_partial);
         else         k_finish<MAXT><<<h->fin_ctas, 128, fin_smem, st>>>(sp, h->d_items + ck.fin.off, ck.fin.cnt, S, w0, w1, h->d_partial);

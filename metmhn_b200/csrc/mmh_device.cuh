@@ -193,6 +193,17 @@ __global__ void k_setup(const SpaceDev* __restrict__ spaces, const Item* __restr
         tab[(uint64_t)ROW_D * NT + u]  = d + dsum;
         tab[(uint64_t)ROW_DP * NT + u] = vdp;
         tab[(uint64_t)ROW_DM * NT + u] = vdm;
+    } else {
+        // product tables: unused rows are zero; for type 2 (dg == 4) rows 30 / 31 hold the two factors of the
+        // PT / MT diagnosis rates (the seeding bit is the top bit of the high part and selects between them)
+        for (int i = sel.nrows; i < NR; ++i) tab[(uint64_t)i * NT + u] = 0.0;
+        if (sel.dg == 4) {
+            double vp = 1.0, vm = 1.0;
+            for (int b = 0; b < KT; ++b) if ((u >> b) & 1u) { vp *= P->dp[sev[b]]; vm *= P->dm[sev[b]]; }
+            if (part) { const bool seeded = (u >> (KT - 1)) & 1u; if (seeded) vp = 0.0; else vm = 0.0; }
+            tab[(uint64_t)ROW_DP * NT + u] = vp;
+            tab[(uint64_t)ROW_DM * NT + u] = vm;
+        }
     }
 }
 
@@ -567,6 +578,113 @@ __global__ void k_stats_b(const SpaceDev* __restrict__ spaces, const Item* __res
 }
 
 // ------------------------------------------------------------------------------------------
+// Single-tumour spaces in product form (K1 low bits, K2 high bits; rate(r,u) = T1[r][lo] T2[r][hi]).
+// Their gradient needs, per table row r, the weighted marginals
+//     H1[r][lo] = sum_hi T2[r][hi] E_r(hi,lo)        H2[r][hi] = sum_lo T1[r][lo] E_r(hi,lo)
+// (a 32 x 2^K2 by 2^K2 x 2^K1 product and its mirror image: this is where the reference spends its
+// n_tot-fold x_partial_Q_y passes, vanilla.py:328-393).  E_r = -g for every row, plus, for the row of an
+// active bit a, the correction c_a(u) = [a in u] g(u) + [a not in u] y(u) x(u + a), g = x y.
+// k_pfin_lo: lane = lo, loop over a slice of hi;  k_pfin_hi: warp = hi, lanes stride over lo.
+// Output layout per space (stP): slices x (NR + KA) x N1 partials, then (NR + KA) x N2.
+template <int MB>
+__global__ void __launch_bounds__(256)
+k_pfin_lo(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, uint32_t count, double* __restrict__ S)
+{
+    const uint32_t wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wg >= count) return;
+    const Item it = items[wg];                          // a = chunk of 32 lo, b = hi slice
+    const SpaceDev& sp = spaces[it.space];
+    const int KA = sp.KA, K1 = sp.splitA, K2 = KA - K1;
+    const uint32_t N1 = 1u << K1, N2 = 1u << K2;
+    const uint32_t lo = (it.a << 5) | lane;
+    const bool valid = lo < N1;
+    const uint32_t per = (N2 + sp.slices - 1) / sp.slices;
+    const uint32_t h0 = it.b * per, h1 = min(N2, h0 + per);
+    const double* x = S + sp.x_off;
+    const double* y = S + sp.y_off;
+    const double* T2 = S + sp.tabA + ((uint64_t)NR << K1);
+    double aR[NR], aC[MB];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) aR[r] = 0.0;
+#pragma unroll
+    for (int a = 0; a < MB; ++a) aC[a] = 0.0;
+    for (uint32_t hi = h0; hi < h1; ++hi) {
+        const uint32_t u = (hi << K1) | lo;
+        const double xv = valid ? x[u] : 0.0, yv = valid ? y[u] : 0.0;
+        const double g = xv * yv;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) aR[r] = fma(T2[((uint64_t)r << K2) + hi], g, aR[r]);
+#pragma unroll
+        for (int a = 0; a < MB; ++a) {
+            if (a < KA) {
+                const uint32_t bit = 1u << a;
+                double xa = 0.0;
+                if (a < 5) xa = __shfl_xor_sync(0xffffffffu, xv, 1 << a);
+                const bool has = (u >> a) & 1u;
+                if (a >= 5 && valid && !has) xa = x[u | bit];
+                const double c = has ? g : yv * xa;
+                aC[a] = fma(T2[((uint64_t)sp.evA[a] << K2) + hi], c, aC[a]);
+            }
+        }
+    }
+    if (!valid) return;
+    double* out = S + sp.stP + (uint64_t)it.b * (NR + KA) * N1;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) out[(uint64_t)r * N1 + lo] = aR[r];
+#pragma unroll
+    for (int a = 0; a < MB; ++a) if (a < KA) out[(uint64_t)(NR + a) * N1 + lo] = aC[a];
+}
+
+template <int MB>
+__global__ void __launch_bounds__(256)
+k_pfin_hi(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, double* __restrict__ S)
+{
+    const Item it = items[blockIdx.x];                  // a = first hi, b = count (one warp each)
+    const SpaceDev& sp = spaces[it.space];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if ((uint32_t)w >= it.b) return;
+    const int KA = sp.KA, K1 = sp.splitA, K2 = KA - K1;
+    const uint32_t N1 = 1u << K1, N2 = 1u << K2;
+    const uint32_t hi = it.a + w;
+    const double* x = S + sp.x_off;
+    const double* y = S + sp.y_off;
+    const double* T1 = S + sp.tabA;
+    double aR[NR], aC[MB];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) aR[r] = 0.0;
+#pragma unroll
+    for (int a = 0; a < MB; ++a) aC[a] = 0.0;
+    for (uint32_t l0 = 0; l0 < N1; l0 += 32) {
+        const uint32_t lo = l0 + lane;
+        const bool valid = lo < N1;
+        const uint32_t u = (hi << K1) | lo;
+        const double xv = valid ? x[u] : 0.0, yv = valid ? y[u] : 0.0;
+        const double g = xv * yv;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) aR[r] = fma(valid ? T1[((uint64_t)r << K1) + lo] : 0.0, g, aR[r]);
+#pragma unroll
+        for (int a = 0; a < MB; ++a) {
+            if (a < KA) {
+                const uint32_t bit = 1u << a;
+                double xa = 0.0;
+                if (a < 5) xa = __shfl_xor_sync(0xffffffffu, xv, 1 << a);
+                const bool has = (u >> a) & 1u;
+                if (a >= 5 && valid && !has) xa = x[u | bit];
+                const double c = has ? g : yv * xa;
+                aC[a] = fma(valid ? T1[((uint64_t)sp.evA[a] << K1) + lo] : 0.0, c, aC[a]);
+            }
+        }
+    }
+    double* out = S + sp.stP + (uint64_t)sp.slices * (NR + KA) * N1;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) { const double t = warp_sum(aR[r]); if (lane == 0) out[(uint64_t)r * N2 + hi] = t; }
+#pragma unroll
+    for (int a = 0; a < MB; ++a)
+        if (a < KA) { const double t = warp_sum(aC[a]); if (lane == 0) out[(uint64_t)(NR + a) * N2 + hi] = t; }
+}
+
+// ------------------------------------------------------------------------------------------
 // Gradient contraction.  lane = table row (event i, or one of the two diagnosis pseudo rows); the warp
 // walks FIN_U sub-states of one group.  For event i not in sub-state u
 //     w_i(u) = T[i][u] * E_i(u),   E_i(u) = sum_other y (x[u + i] - x[u])   (i is a bit of the group)
@@ -591,12 +709,17 @@ k_finish(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, ui
     for (uint32_t k = i0; k < i1; ++k) {
         const Item it = items[k];                     // a = group, b = first sub-state
         const SpaceDev& sp = spaces[it.space];
-        const int g = it.a;
+        const int pmode = it.a >= 2 ? (int)it.a - 1 : 0;     // 0 table mode, 1 product low part, 2 product high part
+        const int g = pmode ? 0 : (int)it.a;
         const bool joint = sp.kind == K_JOINT;
-        const int KG = g ? sp.KB : sp.KA;
+        const int K1 = sp.splitA;
+        const int KG = pmode == 1 ? K1 : pmode == 2 ? sp.KA - K1 : (g ? sp.KB : sp.KA);
         const uint32_t NG = 1u << KG;
-        const uint8_t* ev = g ? sp.evB : sp.evA;
+        const uint8_t* ev = (g ? sp.evB : sp.evA) + (pmode == 2 ? K1 : 0);
         const Side sd = side_of(sp, g, S);
+        const double* ptab = pmode == 2 ? sd.t + ((uint64_t)NR << K1) : sd.t;     // T1 or T2
+        const double* pH = S + sp.stP + (pmode == 2 ? (uint64_t)sp.slices * (NR + sp.KA) * (1u << K1) : 0);
+        const int psl = pmode == 1 ? (int)sp.slices : 1;
         const double* st = S + (g ? sp.stB : sp.stA);
         const double* y = S + sp.y_off;
         const double* x = S + sp.x_off;
@@ -614,8 +737,9 @@ k_finish(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, ui
         const bool is_row = lane < nrows;
         const bool is_pseudo = (lane == ROW_DP || lane == ROW_DM) &&
                                (sp.kind == K_PRE || sp.kind == K_JOINT || sp.kind == K_S2);
-        int abit = -1;
+        int abit = -1, abit_full = -1;                       // bit of this lane's event in the group / in the space
         for (int b = 0; b < KG; ++b) if (ev[b] == lane) abit = b;
+        if (pmode) for (int b = 0; b < sp.KA; ++b) if (sp.evA[b] == lane) abit_full = b;
         const double wgt = sp.cls ? w_other : w_type0;
         double tot = 0.0, ac[MB];
 #pragma unroll
@@ -623,7 +747,17 @@ k_finish(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, ui
         const uint32_t u1 = min(NG, it.b + FIN_U);
         for (uint32_t u = it.b; u < u1; ++u) {
             double wv = 0.0;
-            if (is_row || is_pseudo) {
+            if (pmode) {
+                if (is_row || is_pseudo) {
+                    double hsum = 0.0, csum = 0.0;
+                    const uint64_t slice = (uint64_t)(NR + sp.KA) * NG;
+                    for (int q = 0; q < psl; ++q) {
+                        hsum += pH[q * slice + (uint64_t)lane * NG + u];
+                        if (is_row && abit_full >= 0) csum += pH[q * slice + (uint64_t)(NR + abit_full) * NG + u];
+                    }
+                    wv = ptab[(uint64_t)lane * NG + u] * (csum - hsum);
+                }
+            } else if (is_row || is_pseudo) {
                 const double R = is_row ? sd.rate(lane, u) : sd.special(lane, u);
                 double E;
                 if (joint) {
@@ -657,8 +791,10 @@ k_finish(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, ui
             double* row = G + ((size_t)accid * NR + lane) * NR;
 #pragma unroll
             for (int b = 0; b < MB; ++b) if (b < KG) row[ev[b]] += wgt * ac[b];
-            if (is_row) { row[lane] += wgt * tot; if (always_n) row[n] += wgt * tot; }
-            else if (pseudo_tot) row[n] += wgt * tot;
+            if (pmode != 2) {                                   // totals are counted once (low part)
+                if (is_row) { row[lane] += wgt * tot; if (always_n) row[n] += wgt * tot; }
+                else if (pseudo_tot) row[n] += wgt * tot;
+            }
         }
         __syncwarp();
     }
