@@ -318,71 +318,125 @@ __device__ __forceinline__ double rhs_adj(const SpaceDev& sp, const SpaceDev* __
     }
 }
 
-// One block of 32 consecutive states (lane = low 5 bits).  Edges that add a bit >= 5 read values
-// of blocks finished earlier (same lane, coalesced); the 5 lane bits are resolved inside the warp by
-// popcount sub-levels with shuffles.  Replaces the (k+1)-sweep Jacobi iteration of
-// likelihood.py:231-262 / vanilla.py:269-305 by one exact substitution.
-template <bool ADJ>
-__device__ __forceinline__ void solve_block(const SpaceDev& sp, const SpaceDev* __restrict__ spaces,
-                                            double* __restrict__ S, uint32_t hi, int lane)
+// ------------------------------------------------------------------------------------------
+// Resolvent solve.  Per-space addressing is resolved ONCE per CTA (big tier) / warp (small tier) into a
+// shared-memory context: for every bit the two table-row pointers whose product is the rate of adding
+// that bit, and the pointers of the diagonal parts.  The per-state work is then a handful of loads and
+// FMAs (the first version of this kernel was issue-bound on address arithmetic, profiles/r1_v3*).
+__device__ const double c_one = 1.0;
+__device__ const double c_zero = 0.0;
+
+struct BitDesc {                       // rate(bit, p) = p1[(p >> sh1) & m1] * p2[(p >> sh2) & m2]
+    const double* p1;
+    const double* p2;
+    uint32_t m1, m2;
+    uint32_t sh1, sh2;
+};
+struct SpaceCtx {
+    BitDesc bit[MAXG];
+    const double* dA;                  // diag(s) = dA[s & mA] + dB[(s >> KA) & mB]
+    const double* dB;
+    uint32_t mA, mB;
+    int K, KA;
+};
+
+__device__ __forceinline__ void ctx_build(SpaceCtx& c, const SpaceDev& sp, const double* __restrict__ S, int t)
 {
     const int KA = sp.KA, KB = sp.KB, K = KA + KB;
-    const uint32_t N = 1u << K, NA = 1u << KA;
+    if (t < K) {
+        const int g = t >= KA, b = g ? t - KA : t;
+        const int KG = g ? KB : KA, K1 = g ? sp.splitB : sp.splitA;
+        const uint32_t sh = g ? KA : 0;
+        const int ev = g ? sp.evB[b] : sp.evA[b];
+        const double* base = S + (g ? sp.tabB : sp.tabA);
+        BitDesc d;
+        if (K1 == 0) {
+            d.p1 = base + ((uint64_t)ev << KG); d.sh1 = sh; d.m1 = (1u << KG) - 1u;
+            d.p2 = &c_one; d.sh2 = 0; d.m2 = 0;
+        } else {
+            const int K2 = KG - K1;
+            d.p1 = base + ((uint64_t)ev << K1); d.sh1 = sh; d.m1 = (1u << K1) - 1u;
+            d.p2 = base + ((uint64_t)NR << K1) + ((uint64_t)ev << K2); d.sh2 = sh + K1; d.m2 = (1u << K2) - 1u;
+        }
+        c.bit[t] = d;
+    }
+    if (t == 0) {
+        auto drow = [&](int g) -> const double* {
+            const int KG = g ? KB : KA, K1 = g ? sp.splitB : sp.splitA;
+            const double* base = S + (g ? sp.tabB : sp.tabA);
+            return K1 == 0 ? base + ((uint64_t)ROW_D << KG) : base + ((uint64_t)NR << K1) + ((uint64_t)NR << (KG - K1));
+        };
+        c.dA = drow(0); c.mA = (1u << KA) - 1u;
+        if (sp.kind == K_JOINT) { c.dB = drow(1); c.mB = (1u << KB) - 1u; }
+        else { c.dB = &c_zero; c.mB = 0; }
+        c.K = K; c.KA = KA;
+    }
+}
+
+__device__ __forceinline__ double ctx_rate(const SpaceCtx& c, int a, uint32_t p)
+{
+    const BitDesc& d = c.bit[a];
+    return d.p1[(p >> d.sh1) & d.m1] * d.p2[(p >> d.sh2) & d.m2];
+}
+
+// One block of 32 consecutive states (lane = low 5 bits).  Edges that add a bit >= 5 read values of blocks
+// finished earlier (same lane, coalesced); the 5 lane bits are resolved inside the warp by popcount
+// sub-levels with shuffles.  Replaces the (k+1)-sweep Jacobi iteration of likelihood.py:231-262 /
+// vanilla.py:269-305 by one exact substitution.
+template <bool ADJ>
+__device__ __forceinline__ void solve_block(const SpaceDev& sp, const SpaceDev* __restrict__ spaces, const SpaceCtx& c,
+                                            double* __restrict__ S, uint32_t hi, int lane)
+{
+    const int K = c.K;
     const uint32_t s = (hi << 5) | (uint32_t)lane;
-    const bool valid = s < N;
-    const Side tA = side_of(sp, 0, S), tB = side_of(sp, 1, S);
+    const bool valid = K >= 5 || (uint32_t)lane < (1u << K);
     double* v = S + (ADJ ? sp.x_off : sp.y_off);
     const int nl = K < 5 ? K : 5;
     double acc = 0.0, inv = 0.0;
     double rl[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     if (valid) {
-        double d = tA.special(ROW_D, s & (NA - 1u));
-        if (sp.kind == K_JOINT) d += tB.special(ROW_D, s >> KA);             // also when KB == 0
-        inv = 1.0 / d;
+        inv = 1.0 / (c.dA[s & c.mA] + c.dB[(s >> c.KA) & c.mB]);
         acc = ADJ ? rhs_adj(sp, spaces, S, s) : rhs_fwd(sp, spaces, S, s);
-        for (int a = 5; a < K; ++a) {
+        // bits >= 5: FWD visits the set bits of hi, ADJ the unset ones
+        uint32_t m = ADJ ? (~hi & ((K > 5 ? (1u << (K - 5)) : 1u) - 1u)) : hi;
+        while (m) {
+            const int a = __ffs(m) + 4;
+            m &= m - 1;
             const uint32_t bit = 1u << a;
-            if (!ADJ) {
-                if (s & bit) { const uint32_t p = s ^ bit; acc = fma(rate_of(sp, tA, tB, a, p), v[p], acc); }
-            } else {
-                if (!(s & bit)) acc = fma(rate_of(sp, tA, tB, a, s), v[s | bit], acc);
-            }
+            if (!ADJ) { const uint32_t p = s ^ bit; acc = fma(ctx_rate(c, a, p), v[p], acc); }
+            else      { acc = fma(ctx_rate(c, a, s), v[s | bit], acc); }
         }
 #pragma unroll
         for (int a = 0; a < 5; ++a) {
             if (a < nl) {
                 const uint32_t bit = 1u << a;
-                if (!ADJ) { if (s & bit) rl[a] = rate_of(sp, tA, tB, a, s ^ bit); }
-                else      { if (!(s & bit)) rl[a] = rate_of(sp, tA, tB, a, s); }
+                if (!ADJ) { if (s & bit) rl[a] = ctx_rate(c, a, s ^ bit); }
+                else      { if (!(s & bit)) rl[a] = ctx_rate(c, a, s); }
             }
         }
     }
+    // lane bits: at sub-level l the lanes with popcount l publish their final value; every lane adds what its
+    // neighbours publish (rl is zero for non-edges), so each edge is used exactly once.
     const int pl = __popc(lane);
     double val = 0.0;
     if (!ADJ) {
         for (int l = 0; l <= nl; ++l) {
             if (pl == l) val = acc * inv;
             if (l < nl) {
+                const double pub = (pl == l) ? val : 0.0;
 #pragma unroll
-                for (int a = 0; a < 5; ++a) {
-                    if (a < nl) {
-                        const double t = __shfl_xor_sync(0xffffffffu, val, 1 << a);
-                        if (pl == l + 1 && ((lane >> a) & 1)) acc = fma(rl[a], t, acc);
-                    }
-                }
+                for (int a = 0; a < 5; ++a)
+                    if (a < nl) acc = fma(rl[a], __shfl_xor_sync(0xffffffffu, pub, 1 << a), acc);
             }
         }
     } else {
         for (int l = nl; l >= 0; --l) {
             if (pl == l) val = acc * inv;
             if (l > 0) {
+                const double pub = (pl == l) ? val : 0.0;
 #pragma unroll
-                for (int a = 0; a < 5; ++a) {
-                    if (a < nl) {
-                        const double t = __shfl_xor_sync(0xffffffffu, val, 1 << a);
-                        if (pl == l - 1 && !((lane >> a) & 1)) acc = fma(rl[a], t, acc);
-                    }
-                }
+                for (int a = 0; a < 5; ++a)
+                    if (a < nl) acc = fma(rl[a], __shfl_xor_sync(0xffffffffu, pub, 1 << a), acc);
             }
         }
     }
@@ -392,33 +446,41 @@ __device__ __forceinline__ void solve_block(const SpaceDev& sp, const SpaceDev* 
 // small tier: one warp owns a whole space and walks its blocks in index order (a valid
 // topological order of the lattice: every predecessor has a smaller index).
 template <bool ADJ>
-__global__ void k_solve_small(const SpaceDev* __restrict__ spaces, const uint32_t* __restrict__ list,
-                              uint32_t count, double* __restrict__ S)
+__global__ void __launch_bounds__(256)
+k_solve_small(const SpaceDev* __restrict__ spaces, const uint32_t* __restrict__ list,
+              uint32_t count, double* __restrict__ S)
 {
+    __shared__ SpaceCtx ctx[8];
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
     if (w >= count) return;
     const SpaceDev& sp = spaces[list[w]];
+    ctx_build(ctx[wl], sp, S, lane);
+    __syncwarp();
     const int K = sp.KA + sp.KB;
     const uint32_t nblk = K > 5 ? (1u << (K - 5)) : 1u;
     if (!ADJ) {
-        for (uint32_t hi = 0; hi < nblk; ++hi) { solve_block<false>(sp, spaces, S, hi, lane); __syncwarp(); }
+        for (uint32_t hi = 0; hi < nblk; ++hi) { solve_block<false>(sp, spaces, ctx[wl], S, hi, lane); __syncwarp(); }
     } else {
-        for (uint32_t hi = nblk; hi-- > 0;) { solve_block<true>(sp, spaces, S, hi, lane); __syncwarp(); }
+        for (uint32_t hi = nblk; hi-- > 0;) { solve_block<true>(sp, spaces, ctx[wl], S, hi, lane); __syncwarp(); }
     }
 }
 
 // big tier: one launch per popcount level of the block index; a segment is up to SEGB blocks of one
 // space at that level (popcount-sorted block index table `hs`).
 template <bool ADJ>
-__global__ void k_solve_big(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs,
-                            const uint32_t* __restrict__ hs, double* __restrict__ S)
+__global__ void __launch_bounds__(256)
+k_solve_big(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs,
+            const uint32_t* __restrict__ hs, double* __restrict__ S)
 {
+    __shared__ SpaceCtx ctx;
     const Item sg = segs[blockIdx.x];
     const SpaceDev& sp = spaces[sg.space];
+    ctx_build(ctx, sp, S, threadIdx.x);
+    __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (uint32_t r = w; r < sg.b; r += nw)
-        solve_block<ADJ>(sp, spaces, S, hs[sg.a + r], lane);
+        solve_block<ADJ>(sp, spaces, ctx, S, hs[sg.a + r], lane);
 }
 
 // per-patient log-likelihood (likelihood.py:316,350,384,405,438)
