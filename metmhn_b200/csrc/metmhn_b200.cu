@@ -57,7 +57,15 @@ struct mmh_handle {
     EvalPar* d_par = nullptr;
     double *d_params = nullptr, *d_scratch = nullptr, *d_logp = nullptr, *d_partial = nullptr;
     double *d_diracc = nullptr, *d_tdir = nullptr, *d_out = nullptr, *h_out = nullptr;
-    cudaStream_t stream = nullptr;
+    // Chunks are independent, so they are spread round-robin over NS side streams, each with its own scratch
+    // buffer and gradient partials: the thin popcount levels and the tails of one chunk overlap with the work
+    // of the others.  Chunk -> stream is static and k_final adds the slots in a fixed order: results stay
+    // bit-identical from call to call.
+    static constexpr int NS = 3;
+    cudaStream_t stream = nullptr;               // main stream: parameters, k_prep, k_final, copies
+    cudaStream_t side[NS] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_side[NS] = {nullptr, nullptr, nullptr}, ev_prep = nullptr;
+    double* d_scratch_s[NS] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int fin_ctas = 0;
     int profile = 0;
@@ -401,20 +409,26 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
     const size_t npar = (size_t)h->n_tot * (h->n_tot + 2);
     CK(cudaMalloc((void**)&h->d_par, sizeof(EvalPar)));
     CK(cudaMalloc((void**)&h->d_params, npar * sizeof(double)));
-    CK(cudaMalloc((void**)&h->d_scratch, std::max<uint64_t>(max_scratch, 4) * sizeof(double)));
+    for (int q = 0; q < mmh_handle::NS; ++q) {
+        CK(cudaMalloc((void**)&h->d_scratch_s[q], std::max<uint64_t>(max_scratch, 4) * sizeof(double)));
+        CK(cudaStreamCreateWithFlags(&h->side[q], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->ev_side[q], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&h->ev_prep, cudaEventDisableTiming));
+    h->d_scratch = h->d_scratch_s[0];
     CK(cudaMalloc((void**)&h->d_logp, std::max<int64_t>(n_dat, 1) * sizeof(double)));
     CK(cudaMemset(h->d_logp, 0, std::max<int64_t>(n_dat, 1) * sizeof(double)));
-    CK(cudaMalloc((void**)&h->d_partial, (size_t)h->fin_ctas * NACC * NR * NR * sizeof(double)));
-    CK(cudaMalloc((void**)&h->d_diracc, 2 * NR * sizeof(double)));
-    CK(cudaMalloc((void**)&h->d_tdir, std::max<uint32_t>(h->max_joints, 1) * 2 * sizeof(double)));
+    CK(cudaMalloc((void**)&h->d_partial, (size_t)mmh_handle::NS * h->fin_ctas * NACC * NR * NR * sizeof(double)));
+    CK(cudaMalloc((void**)&h->d_diracc, (size_t)mmh_handle::NS * 2 * NR * sizeof(double)));
+    CK(cudaMalloc((void**)&h->d_tdir, (size_t)mmh_handle::NS * std::max<uint32_t>(h->max_joints, 1) * 2 * sizeof(double)));
     CK(cudaMalloc((void**)&h->d_out, (npar + 1) * sizeof(double)));
     CK(cudaMallocHost((void**)&h->h_out, (npar + 1) * sizeof(double)));
-    CK(cudaStreamCreate(&h->stream));
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
     CK(cudaFuncSetAttribute(k_finish<MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * NACC * NR * NR * (int)sizeof(double)));
     CK(cudaFuncSetAttribute(k_finish<MAXG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * NACC * NR * NR * (int)sizeof(double)));
-    h->st.scratch_bytes = (double)max_scratch * 8.0;
+    h->st.scratch_bytes = (double)max_scratch * 8.0 * mmh_handle::NS;
     *out = h;
     return MMH_OK;
 }
@@ -424,6 +438,8 @@ static int run_eval(mmh_handle* h, const double* d_params, double w0, double w1,
 {
     CK(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
+    constexpr int NS = mmh_handle::NS;
+    const int ns = h->profile ? 1 : NS;                 // profile mode serialises everything on the main stream
     int64_t launches = 0;
     // optional per-class timing (profile mode): CUDA events around every launch group
     size_t evn = 0;
@@ -438,11 +454,25 @@ static int run_eval(mmh_handle* h, const double* d_params, double w0, double w1,
     tick(5);
     k_prep<<<1, 1024, 0, st>>>(d_params, h->n_tot, h->d_par); ++launches;
     if (want_grad) {
-        CK(cudaMemsetAsync(h->d_partial, 0, (size_t)h->fin_ctas * NACC * NR * NR * sizeof(double), st));
-        CK(cudaMemsetAsync(h->d_diracc, 0, 2 * NR * sizeof(double), st));
+        CK(cudaMemsetAsync(h->d_partial, 0, (size_t)NS * h->fin_ctas * NACC * NR * NR * sizeof(double), st));
+        CK(cudaMemsetAsync(h->d_diracc, 0, (size_t)NS * 2 * NR * sizeof(double), st));
     }
-    double* S = h->d_scratch;
+    const cudaStream_t main_stream = st;
+    if (ns > 1) {
+        CK(cudaEventRecord(h->ev_prep, main_stream));
+        for (int q = 0; q < ns; ++q) CK(cudaStreamWaitEvent(h->side[q], h->ev_prep, 0));
+    }
+    const size_t part_stride = (size_t)h->fin_ctas * NACC * NR * NR;
+    const size_t tdir_stride = (size_t)std::max<uint32_t>(h->max_joints, 1) * 2;
+    size_t chunk_no = 0;
     for (const ChunkPlan& ck : h->chunks) {
+        const int slot = ns > 1 ? (int)(chunk_no % ns) : 0;
+        ++chunk_no;
+        st = ns > 1 ? h->side[slot] : main_stream;
+        double* S = h->d_scratch_s[slot];
+        double* d_partial = h->d_partial + slot * part_stride;
+        double* d_diracc = h->d_diracc + (size_t)slot * 2 * NR;
+        double* d_tdir = h->d_tdir + slot * tdir_stride;
         const SpaceDev* sp = h->d_spaces + ck.space0;
         auto small = [&](const Range& r, bool adj) {
             if (!r.cnt) return;
@@ -478,8 +508,8 @@ static int run_eval(mmh_handle* h, const double* d_params, double w0, double w1,
         big(ck.sec_lv, true);
         tick(5);
         if (ck.joints.cnt) {
-            k_direct<<<(ck.joints.cnt + 255) / 256, 256, 0, st>>>(sp, h->d_lists + ck.joints.off, ck.joints.cnt, S, h->d_tdir);
-            k_direct_acc<<<dim3(h->n_tot, 2), 256, 0, st>>>(sp, h->d_lists + ck.joints.off, ck.joints.cnt, h->d_tdir, w1, h->d_diracc);
+            k_direct<<<(ck.joints.cnt + 255) / 256, 256, 0, st>>>(sp, h->d_lists + ck.joints.off, ck.joints.cnt, S, d_tdir);
+            k_direct_acc<<<dim3(h->n_tot, 2), 256, 0, st>>>(sp, h->d_lists + ck.joints.off, ck.joints.cnt, d_tdir, w1, d_diracc);
             launches += 2;
         }
         tick(2);
@@ -507,12 +537,18 @@ static int run_eval(mmh_handle* h, const double* d_params, double w0, double w1,
             launches += 2;
         }
         const size_t fin_smem = 4 * NACC * NR * NR * sizeof(double);
-        if (ck.wide) k_finish<MAXG><<<h->fin_ctas, 128, fin_smem, st>>>(sp, h->d_items + ck.fin.off, ck.fin.cnt, S, w0, w1, h->d_partial);
-        else         k_finish<MAXT><<<h->fin_ctas, 128, fin_smem, st>>>(sp, h->d_items + ck.fin.off, ck.fin.cnt, S, w0, w1, h->d_partial);
+        if (ck.wide) k_finish<MAXG><<<h->fin_ctas, 128, fin_smem, st>>>(sp, h->d_items + ck.fin.off, ck.fin.cnt, S, w0, w1, d_partial);
+        else         k_finish<MAXT><<<h->fin_ctas, 128, fin_smem, st>>>(sp, h->d_items + ck.fin.off, ck.fin.cnt, S, w0, w1, d_partial);
         ++launches;
     }
+    st = main_stream;
+    if (ns > 1)
+        for (int q = 0; q < ns; ++q) {
+            CK(cudaEventRecord(h->ev_side[q], h->side[q]));
+            CK(cudaStreamWaitEvent(main_stream, h->ev_side[q], 0));
+        }
     tick(5);
-    k_final<<<1, 1024, 0, st>>>(h->d_partial, h->fin_ctas, h->d_diracc, h->d_logp, h->d_cls, h->n_dat, h->d_cnt, w0, w1,
+    k_final<<<1, 1024, 0, st>>>(h->d_partial, NS * h->fin_ctas, h->d_diracc, NS, h->d_logp, h->d_cls, h->n_dat, h->d_cnt, w0, w1,
                                 h->n_tot, want_grad, h->d_out);
     ++launches;
     tick(-1);
@@ -631,7 +667,13 @@ extern "C" void mmh_destroy(mmh_handle* h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaFree(h->d_spaces); cudaFree(h->d_lists); cudaFree(h->d_items); cudaFree(h->d_hs); cudaFree(h->d_cls);
-    cudaFree(h->d_cnt); cudaFree(h->d_par); cudaFree(h->d_params); cudaFree(h->d_scratch); cudaFree(h->d_logp);
+    cudaFree(h->d_cnt); cudaFree(h->d_par); cudaFree(h->d_params); cudaFree(h->d_logp);
+    for (int q = 0; q < mmh_handle::NS; ++q) {
+        cudaFree(h->d_scratch_s[q]);
+        if (h->side[q]) cudaStreamDestroy(h->side[q]);
+        if (h->ev_side[q]) cudaEventDestroy(h->ev_side[q]);
+    }
+    if (h->ev_prep) cudaEventDestroy(h->ev_prep);
     cudaFree(h->d_partial); cudaFree(h->d_diracc); cudaFree(h->d_tdir); cudaFree(h->d_out);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->stream) cudaStreamDestroy(h->stream);

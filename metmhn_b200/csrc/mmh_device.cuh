@@ -874,7 +874,7 @@ k_finish(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, ui
 // (log_theta, log_d_p, log_d_m) and add the weighted log-likelihood sum.
 //   theta_pt/d_p space (likelihood.py:457-461, 605-609): theta_ij += G1 except (i<n, j=n);  d_p[j] -= sum_{i!=j} G1[i][j]
 //   theta/d_m space    (likelihood.py:565-566):          theta_ij += G2;                    d_m[j] -= sum_{i!=j} G2[i][j]
-__global__ void k_final(const double* __restrict__ partial, int n_cta, const double* __restrict__ diracc,
+__global__ void k_final(const double* __restrict__ partial, int n_cta, const double* __restrict__ diracc, int n_dir,
                         const double* __restrict__ logp, const uint8_t* __restrict__ cls, int64_t n_dat,
                         const double* __restrict__ cnt_dm2, double w_type0, double w_other, int n_tot,
                         int want_grad, double* __restrict__ out)
@@ -912,8 +912,8 @@ __global__ void k_final(const double* __restrict__ partial, int n_cta, const dou
         gth[t] = v;
     }
     for (int j = threadIdx.x; j < n_tot; j += blockDim.x) {
-        double a = G[0][ROW_DP][j] + diracc[j];
-        double b = G[0][ROW_DM][j] + diracc[NR + j] + w_other * cnt_dm2[j];
+        double a = G[0][ROW_DP][j], b = G[0][ROW_DM][j] + w_other * cnt_dm2[j];
+        for (int q = 0; q < n_dir; ++q) { a += diracc[q * 2 * NR + j]; b += diracc[q * 2 * NR + NR + j]; }
         for (int i = 0; i < n_tot; ++i) if (i != j) { a -= G[1][i][j]; b -= G[2][i][j]; }
         gdp[j] = a; gdm[j] = b;
     }
