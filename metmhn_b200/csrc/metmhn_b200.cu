@@ -61,11 +61,12 @@ struct mmh_handle {
     // buffer and gradient partials: the thin popcount levels and the tails of one chunk overlap with the work
     // of the others.  Chunk -> stream is static and k_final adds the slots in a fixed order: results stay
     // bit-identical from call to call.
-    static constexpr int NS = 3;
+    static constexpr int NS = 8;                 // slots allocated; `ns` of them are used (MMH_STREAMS, default 6)
+    int ns = 6;
     cudaStream_t stream = nullptr;               // main stream: parameters, k_prep, k_final, copies
-    cudaStream_t side[NS] = {nullptr, nullptr, nullptr};
-    cudaEvent_t ev_side[NS] = {nullptr, nullptr, nullptr}, ev_prep = nullptr;
-    double* d_scratch_s[NS] = {nullptr, nullptr, nullptr};
+    cudaStream_t side[NS] = {};
+    cudaEvent_t ev_side[NS] = {}, ev_prep = nullptr;
+    double* d_scratch_s[NS] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int fin_ctas = 0;
     int profile = 0;
@@ -341,7 +342,7 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
         ck.st_a.off = items.size();
         for (uint32_t i = 0; i < ck.nspaces; ++i)
             if (sp[i].kind == K_JOINT) {
-                const uint32_t nblk = std::max<uint32_t>(1u, (1u << sp[i].KA) >> 5);
+                const uint32_t nblk = std::max<uint32_t>(1u, (1u << sp[i].KA) >> 6);     // chunks of 64 uA
                 for (uint32_t sl = 0; sl < sp[i].slices; ++sl)
                     for (uint32_t b = 0; b < nblk; ++b) items.push_back({i, b, sl});
             }
@@ -409,7 +410,9 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
     const size_t npar = (size_t)h->n_tot * (h->n_tot + 2);
     CK(cudaMalloc((void**)&h->d_par, sizeof(EvalPar)));
     CK(cudaMalloc((void**)&h->d_params, npar * sizeof(double)));
-    for (int q = 0; q < mmh_handle::NS; ++q) {
+    if (const char* e = std::getenv("MMH_STREAMS")) h->ns = std::max(1, std::min((int)mmh_handle::NS, std::atoi(e)));
+    h->ns = (int)std::max<size_t>(1, std::min<size_t>((size_t)h->ns, h->chunks.size()));
+    for (int q = 0; q < h->ns; ++q) {
         CK(cudaMalloc((void**)&h->d_scratch_s[q], std::max<uint64_t>(max_scratch, 4) * sizeof(double)));
         CK(cudaStreamCreateWithFlags(&h->side[q], cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&h->ev_side[q], cudaEventDisableTiming));
@@ -428,7 +431,7 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
     CK(cudaEventCreate(&h->ev1));
     CK(cudaFuncSetAttribute(k_finish<MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * NACC * NR * NR * (int)sizeof(double)));
     CK(cudaFuncSetAttribute(k_finish<MAXG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * NACC * NR * NR * (int)sizeof(double)));
-    h->st.scratch_bytes = (double)max_scratch * 8.0 * mmh_handle::NS;
+    h->st.scratch_bytes = (double)max_scratch * 8.0 * h->ns;
     *out = h;
     return MMH_OK;
 }
@@ -439,7 +442,7 @@ static int run_eval(mmh_handle* h, const double* d_params, double w0, double w1,
     CK(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     constexpr int NS = mmh_handle::NS;
-    const int ns = h->profile ? 1 : NS;                 // profile mode serialises everything on the main stream
+    const int ns = h->profile ? 1 : h->ns;              // profile mode serialises everything on the main stream
     int64_t launches = 0;
     // optional per-class timing (profile mode): CUDA events around every launch group
     size_t evn = 0;
@@ -518,11 +521,9 @@ static int run_eval(mmh_handle* h, const double* d_params, double w0, double w1,
         small(ck.pre, true);
         tick(3);
         if (ck.st_a.cnt) {
-            if (ck.wide) k_stats_a<MAXG><<<(ck.st_a.cnt + 7) / 8, 256, 0, st>>>(sp, h->d_items + ck.st_a.off, ck.st_a.cnt, S);
-            else         k_stats_a<MAXT><<<(ck.st_a.cnt + 7) / 8, 256, 0, st>>>(sp, h->d_items + ck.st_a.off, ck.st_a.cnt, S);
+            k_stats_a<<<(ck.st_a.cnt + 7) / 8, 256, 0, st>>>(sp, h->d_items + ck.st_a.off, ck.st_a.cnt, S);
             k_stats_a_reduce<<<ck.st_ar.cnt, 1024, 0, st>>>(sp, h->d_items + ck.st_ar.off, S);
-            if (ck.wide) k_stats_b<MAXG><<<ck.st_b.cnt, 256, 0, st>>>(sp, h->d_items + ck.st_b.off, S);
-            else         k_stats_b<MAXT><<<ck.st_b.cnt, 256, 0, st>>>(sp, h->d_items + ck.st_b.off, S);
+            k_stats_b<<<ck.st_b.cnt, 256, 0, st>>>(sp, h->d_items + ck.st_b.off, S);
             launches += 3;
         }
         tick(4);

@@ -549,47 +549,66 @@ __global__ void k_direct_acc(const SpaceDev* __restrict__ spaces, const uint32_t
 //   stA[1+a][uA] = sum_uB y[uB,uA] x[uB,uA|a]     stB[1+a][uB] = sum_uA y[uB,uA] x[uB|a,uA]
 // They are all the joint pass has to deliver: every theta / d_p / d_m gradient entry is a
 // contraction of these small tables with the group rate tables (k_finish).
-template <int MB>                                     // MB = 16 (narrow chunks) or MAXG
-__global__ void k_stats_a(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, uint32_t count,
-                          double* __restrict__ S)
+// group-A statistics: a lane owns TWO consecutive uA (16-byte loads), a warp 64; bit 0 is resolved inside the
+// lane, bits 1..5 with shuffles, higher bits by a loop over the bits that are free in this chunk.
+__global__ void __launch_bounds__(256)
+k_stats_a(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, uint32_t count, double* __restrict__ S)
 {
     const uint32_t wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (wg >= count) return;
-    const Item it = items[wg];                       // a = block of 32 uA, b = slice
+    const Item it = items[wg];                       // a = chunk of 64 uA, b = slice
     const SpaceDev& sp = spaces[it.space];
     const int KA = sp.KA;
     const uint32_t NA = 1u << KA, NB = 1u << sp.KB;
-    const uint32_t uA = (it.a << 5) | lane;
-    const bool valid = uA < NA;
     const uint32_t per = (NB + sp.slices - 1) / sp.slices;
     const uint32_t b0 = it.b * per, b1 = min(NB, b0 + per);
     const double* y = S + sp.y_off;
     const double* x = S + sp.x_off;
-    constexpr int AH = MB - 5;
-    double g = 0.0, aL[5] = {0, 0, 0, 0, 0}, aH[AH];
-#pragma unroll
-    for (int a = 0; a < AH; ++a) aH[a] = 0.0;
+    double* out = S + sp.stP + (uint64_t)it.b * (KA + 1) * NA;
+    if (KA == 0) {                                   // a single uA: only g
+        if (lane == 0) { double g = 0.0; for (uint32_t uB = b0; uB < b1; ++uB) g = fma(x[uB], y[uB], g); out[0] = g; }
+        return;
+    }
+    const uint32_t uA = (it.a << 6) | (lane << 1);   // first of the two states of this lane
+    const bool valid = uA < NA;
+    double g0 = 0.0, g1 = 0.0, a0 = 0.0;             // bit 0: only the even state lacks it
+    double l0[5] = {0, 0, 0, 0, 0}, l1[5] = {0, 0, 0, 0, 0};
     for (uint32_t uB = b0; uB < b1; ++uB) {
         const uint64_t s = ((uint64_t)uB << KA) | uA;
-        const double yv = valid ? y[s] : 0.0, xv = valid ? x[s] : 0.0;
-        g = fma(xv, yv, g);
+        double2 yv = make_double2(0.0, 0.0), xv = yv;
+        if (valid) { yv = *reinterpret_cast<const double2*>(y + s); xv = *reinterpret_cast<const double2*>(x + s); }
+        g0 = fma(xv.x, yv.x, g0); g1 = fma(xv.y, yv.y, g1);
+        a0 = fma(yv.x, xv.y, a0);
 #pragma unroll
-        for (int a = 0; a < 5; ++a) {
-            const double xa = __shfl_xor_sync(0xffffffffu, xv, 1 << a);
-            if (a < KA && !((lane >> a) & 1)) aL[a] = fma(yv, xa, aL[a]);
+        for (int a = 1; a <= 5; ++a) {
+            const double px = __shfl_xor_sync(0xffffffffu, xv.x, 1 << (a - 1));
+            const double py = __shfl_xor_sync(0xffffffffu, xv.y, 1 << (a - 1));
+            if (a < KA && !((lane >> (a - 1)) & 1)) { l0[a - 1] = fma(yv.x, px, l0[a - 1]); l1[a - 1] = fma(yv.y, py, l1[a - 1]); }
         }
-#pragma unroll
-        for (int a = 0; a < AH; ++a)
-            if (a + 5 < KA && valid && !((uA >> (a + 5)) & 1u)) aH[a] = fma(yv, x[s | (1ull << (a + 5))], aH[a]);
     }
-    if (!valid) return;
-    double* out = S + sp.stP + (uint64_t)it.b * (KA + 1) * NA;
-    out[uA] = g;
+    if (valid) {
+        out[uA] = g0; out[uA + 1] = g1;
+        out[(uint64_t)NA + uA] = a0; out[(uint64_t)NA + uA + 1] = 0.0;
 #pragma unroll
-    for (int a = 0; a < 5; ++a) if (a < KA) out[(uint64_t)(1 + a) * NA + uA] = aL[a];
-#pragma unroll
-    for (int a = 0; a < AH; ++a) if (a + 5 < KA) out[(uint64_t)(6 + a) * NA + uA] = aH[a];
+        for (int a = 1; a <= 5; ++a)
+            if (a < KA) { out[(uint64_t)(1 + a) * NA + uA] = l0[a - 1]; out[(uint64_t)(1 + a) * NA + uA + 1] = l1[a - 1]; }
+    }
+    // bits >= 6: uniform over the chunk; y is re-read from L1
+    for (int a = 6; a < KA; ++a) {
+        if (!valid) break;
+        double h0 = 0.0, h1 = 0.0;
+        if (!((uA >> a) & 1u)) {
+            const uint64_t bit = 1ull << a;
+            for (uint32_t uB = b0; uB < b1; ++uB) {
+                const uint64_t s = ((uint64_t)uB << KA) | uA;
+                const double2 yv = *reinterpret_cast<const double2*>(y + s);
+                const double2 xa = *reinterpret_cast<const double2*>(x + (s | bit));
+                h0 = fma(yv.x, xa.x, h0); h1 = fma(yv.y, xa.y, h1);
+            }
+        }
+        out[(uint64_t)(1 + a) * NA + uA] = h0; out[(uint64_t)(1 + a) * NA + uA + 1] = h1;
+    }
 }
 
 __global__ void k_stats_a_reduce(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items,
@@ -605,9 +624,32 @@ __global__ void k_stats_a_reduce(const SpaceDev* __restrict__ spaces, const Item
     S[sp.stA + t] = s;
 }
 
-template <int MB>
-__global__ void k_stats_b(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items,
-                          double* __restrict__ S)
+// group-B statistics: one warp per uB; dot products of the y row with the x rows of up to four free bits at a
+// time, 16-byte loads.
+__device__ __forceinline__ void row_dots4(const double* __restrict__ yr, const double* const (&xr)[4], uint32_t NA, int lane,
+                                          double (&acc)[4])
+{
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] = 0.0;
+    if (NA >= 2) {
+        for (uint32_t i = 2 * lane; i < NA; i += 64) {
+            const double2 yv = *reinterpret_cast<const double2*>(yr + i);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double2 xv = *reinterpret_cast<const double2*>(xr[q] + i);
+                acc[q] = fma(yv.x, xv.x, acc[q]); acc[q] = fma(yv.y, xv.y, acc[q]);
+            }
+        }
+    } else if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] = yr[0] * xr[q][0];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] = warp_sum(acc[q]);
+}
+
+__global__ void __launch_bounds__(256)
+k_stats_b(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, double* __restrict__ S)
 {
     const Item it = items[blockIdx.x];               // a = first uB, b = count (one warp each)
     const SpaceDev& sp = spaces[it.space];
@@ -616,27 +658,33 @@ __global__ void k_stats_b(const SpaceDev* __restrict__ spaces, const Item* __res
     const int KA = sp.KA, KB = sp.KB;
     const uint32_t NA = 1u << KA, NB = 1u << KB;
     const uint32_t uB = it.a + w;
-    const double* y = S + sp.y_off + ((uint64_t)uB << KA);
-    const double* x = S + sp.x_off + ((uint64_t)uB << KA);
-    double g = 0.0, ac[MB];
-#pragma unroll
-    for (int a = 0; a < MB; ++a) ac[a] = 0.0;
-    for (uint32_t uA = lane; uA < NA; uA += 32) {
-        const double yv = y[uA];
-        g = fma(x[uA], yv, g);
-#pragma unroll
-        for (int a = 0; a < MB; ++a)
-            if (a < KB && !((uB >> a) & 1u)) ac[a] = fma(yv, x[((uint64_t)1 << (a + KA)) + uA], ac[a]);
-    }
+    const double* yr = S + sp.y_off + ((uint64_t)uB << KA);
+    const double* xb = S + sp.x_off;
     double* out = S + sp.stB;
-    g = warp_sum(g);
-    if (lane == 0) out[uB] = g;
-#pragma unroll
-    for (int a = 0; a < MB; ++a)
-        if (a < KB) {
-            const double t = warp_sum(ac[a]);
-            if (lane == 0) out[(uint64_t)(1 + a) * NB + uB] = t;
+    // row 0 (g = sum x y) travels with the first group of free bits
+    int rows[4] = {0, -1, -1, -1};
+    int nrow = 1;
+    for (int a = 0; a <= KB; ++a) {
+        const bool last = (a == KB);
+        if (!last) {
+            if ((uB >> a) & 1u) { if (lane == 0) out[(uint64_t)(1 + a) * NB + uB] = 0.0; }
+            else rows[nrow++] = 1 + a;
         }
+        if (nrow == 4 || (last && nrow > 0)) {
+            const double* xr[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int r = q < nrow ? rows[q] : 0;
+                xr[q] = xb + ((uint64_t)(r == 0 ? uB : (uB | (1u << (r - 1)))) << KA);
+            }
+            double acc[4];
+            row_dots4(yr, xr, NA, lane, acc);
+            if (lane == 0)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (q < nrow) out[(uint64_t)rows[q] * NB + uB] = acc[q];
+            nrow = 0;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
