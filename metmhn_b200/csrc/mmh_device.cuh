@@ -23,7 +23,7 @@ constexpr int MAXT    = 16;   // bits per group with one explicit table; wider g
 constexpr int MAXG    = 26;   // bits per group
 constexpr int BIGK    = 13;   // spaces with K >= BIGK are solved by per-level launches
 constexpr int SEGB    = 32;   // blocks of 32 states per big-tier segment (one CTA)
-constexpr int FIN_U   = 256;  // sub-states per finish work item
+constexpr int FIN_U   = 64;   // sub-states per finish work item
 
 enum Kind : uint8_t { K_PRE = 0, K_JOINT = 1, K_PF = 2, K_MF = 3, K_S1 = 4, K_S2 = 5 };
 
