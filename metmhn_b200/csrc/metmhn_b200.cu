@@ -31,6 +31,7 @@ struct Range { uint64_t off = 0; uint32_t cnt = 0; };
 struct ChunkPlan {
     uint64_t space0 = 0;
     uint32_t nspaces = 0;
+    Range pre4, main_small4, sec_small4;         // small-tier spaces with K >= 7 (four states per lane)
     Range setup, setup_wide, pre, main_small, sec_small, logp, joints, st_a, st_ar, st_b, pf_lo, pf_hi, fin;
     bool wide = false;                           // some group has more than MAXT bits
     std::vector<Range> main_lv, sec_lv;          // big-tier segments per popcount level
@@ -295,9 +296,12 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
         auto is_main = [](const SpaceDev& s) { return s.kind == K_JOINT || s.kind == K_S1 || s.kind == K_S2; };
         auto is_sec = [](const SpaceDev& s) { return s.kind == K_PF || s.kind == K_MF; };
         auto bits = [](const SpaceDev& s) { return (int)s.KA + (int)s.KB; };
-        ck.pre = list_of([&](const SpaceDev& s) { return s.kind == K_PRE; });
-        ck.main_small = list_of([&](const SpaceDev& s) { return is_main(s) && bits(s) < BIGK; });
-        ck.sec_small = list_of([&](const SpaceDev& s) { return is_sec(s) && bits(s) < BIGK; });
+        ck.pre = list_of([&](const SpaceDev& s) { return s.kind == K_PRE && bits(s) < 7; });
+        ck.main_small = list_of([&](const SpaceDev& s) { return is_main(s) && bits(s) < 7; });
+        ck.sec_small = list_of([&](const SpaceDev& s) { return is_sec(s) && bits(s) < 7; });
+        ck.pre4 = list_of([&](const SpaceDev& s) { return s.kind == K_PRE && bits(s) >= 7; });
+        ck.main_small4 = list_of([&](const SpaceDev& s) { return is_main(s) && bits(s) >= 7 && bits(s) < BIGK; });
+        ck.sec_small4 = list_of([&](const SpaceDev& s) { return is_sec(s) && bits(s) >= 7 && bits(s) < BIGK; });
         ck.logp = list_of([&](const SpaceDev& s) { return is_main(s); });
         ck.joints = list_of([&](const SpaceDev& s) { return s.kind == K_JOINT; });
         h->max_joints = std::max(h->max_joints, ck.joints.cnt);
@@ -320,14 +324,14 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
         ck.setup_wide.cnt = (uint32_t)(items.size() - ck.setup_wide.off);
         auto levels_of = [&](auto pred, std::vector<Range>& lv) {
             int maxkh = -1;
-            for (uint32_t i = 0; i < ck.nspaces; ++i) if (pred(sp[i]) && bits(sp[i]) >= BIGK) maxkh = std::max(maxkh, bits(sp[i]) - 5);
+            for (uint32_t i = 0; i < ck.nspaces; ++i) if (pred(sp[i]) && bits(sp[i]) >= BIGK) maxkh = std::max(maxkh, bits(sp[i]) - 7);
             if (maxkh < 0) return;
             lv.resize(maxkh + 1);
             for (int l = 0; l <= maxkh; ++l) {
                 lv[l].off = items.size();
                 for (uint32_t i = 0; i < ck.nspaces; ++i) {
                     if (!pred(sp[i]) || bits(sp[i]) < BIGK) continue;
-                    const int kh = bits(sp[i]) - 5;
+                    const int kh = bits(sp[i]) - 7;          // blocks of 128 states
                     if (l > kh) continue;
                     need_hs(kh);
                     const uint32_t a = hs_lvl[kh][l], b = hs_lvl[kh][l + 1];
@@ -484,13 +488,20 @@ static int run_eval(mmh_handle* h, const double* d_params, double w0, double w1,
             else     k_solve_small<false><<<grid, 256, 0, st>>>(sp, h->d_lists + r.off, r.cnt, S);
             ++launches;
         };
+        auto small4 = [&](const Range& r, bool adj) {
+            if (!r.cnt) return;
+            const uint32_t grid = (r.cnt + 7) / 8;
+            if (adj) k_solve_small4<true><<<grid, 256, 0, st>>>(sp, h->d_lists + r.off, r.cnt, S);
+            else     k_solve_small4<false><<<grid, 256, 0, st>>>(sp, h->d_lists + r.off, r.cnt, S);
+            ++launches;
+        };
         auto big = [&](const std::vector<Range>& lv, bool adj) {
             const int L = (int)lv.size();
             for (int q = 0; q < L; ++q) {
                 const Range& r = lv[adj ? L - 1 - q : q];
                 if (!r.cnt) continue;
-                if (adj) k_solve_big<true><<<r.cnt, 256, 0, st>>>(sp, h->d_items + r.off, h->d_hs, S);
-                else     k_solve_big<false><<<r.cnt, 256, 0, st>>>(sp, h->d_items + r.off, h->d_hs, S);
+                if (adj) k_solve_big4<true><<<r.cnt, 256, 0, st>>>(sp, h->d_items + r.off, h->d_hs, S);
+                else     k_solve_big4<false><<<r.cnt, 256, 0, st>>>(sp, h->d_items + r.off, h->d_hs, S);
                 ++launches;
             }
         };
@@ -498,16 +509,16 @@ static int run_eval(mmh_handle* h, const double* d_params, double w0, double w1,
         k_setup<<<ck.setup.cnt, 256, 0, st>>>(sp, h->d_items + ck.setup.off, h->d_par, S); ++launches;
         if (ck.setup_wide.cnt) { k_setup_wide<<<ck.setup_wide.cnt, 1024, 0, st>>>(sp, h->d_items + ck.setup_wide.off, h->d_par, S); ++launches; }
         tick(1);
-        small(ck.pre, false);
-        small(ck.main_small, false);
+        small(ck.pre, false); small4(ck.pre4, false);
+        small(ck.main_small, false); small4(ck.main_small4, false);
         big(ck.main_lv, false);
-        small(ck.sec_small, false);
+        small(ck.sec_small, false); small4(ck.sec_small4, false);
         big(ck.sec_lv, false);
         tick(5);
         if (ck.logp.cnt) { k_logp<<<(ck.logp.cnt + 127) / 128, 128, 0, st>>>(sp, h->d_lists + ck.logp.off, ck.logp.cnt, S, h->d_logp); ++launches; }
         if (!want_grad) continue;
         tick(2);
-        small(ck.sec_small, true);
+        small(ck.sec_small, true); small4(ck.sec_small4, true);
         big(ck.sec_lv, true);
         tick(5);
         if (ck.joints.cnt) {
@@ -516,9 +527,9 @@ static int run_eval(mmh_handle* h, const double* d_params, double w0, double w1,
             launches += 2;
         }
         tick(2);
-        small(ck.main_small, true);
+        small(ck.main_small, true); small4(ck.main_small4, true);
         big(ck.main_lv, true);
-        small(ck.pre, true);
+        small(ck.pre, true); small4(ck.pre4, true);
         tick(3);
         if (ck.st_a.cnt) {
             k_stats_a<<<(ck.st_a.cnt + 7) / 8, 256, 0, st>>>(sp, h->d_items + ck.st_a.off, ck.st_a.cnt, S);

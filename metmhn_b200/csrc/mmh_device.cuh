@@ -483,6 +483,158 @@ k_solve_big(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs,
         solve_block<ADJ>(sp, spaces, ctx, S, hs[sg.a + r], lane);
 }
 
+// ------------------------------------------------------------------------------------------
+// Four states per lane.  A warp owns 128 consecutive states: bits 0,1 live inside the lane (registers),
+// bits 2..6 across the lanes, bits >= 7 select the block.  The index arithmetic of an edge bit is done once
+// per four states and the table rows / vectors are read with 16-byte loads (still fully coalesced: a warp reads
+// 1 KB of consecutive addresses).  Needs K >= 7; smaller spaces use solve_block.
+__device__ __forceinline__ void factor4(const double* __restrict__ p, uint32_t sh, uint32_t m, uint32_t p0, double (&f)[4])
+{
+    if (sh >= 2 || m == 0) {                                   // constant over the four states
+        const double c = p[(p0 >> sh) & m];
+        f[0] = c; f[1] = c; f[2] = c; f[3] = c;
+    } else if (sh == 0 && m >= 3u) {                           // contiguous
+        const double2* q = reinterpret_cast<const double2*>(p + (p0 & m));
+        const double2 a = q[0], b = q[1];
+        f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+    } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) f[t] = p[((p0 + t) >> sh) & m];
+    }
+}
+__device__ __forceinline__ void rate4(const BitDesc& d, uint32_t p0, double (&r)[4])
+{
+    factor4(d.p1, d.sh1, d.m1, p0, r);
+    if (d.p2 != &c_one) {
+        double g[4];
+        factor4(d.p2, d.sh2, d.m2, p0, g);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) r[t] *= g[t];
+    }
+}
+
+template <bool ADJ>
+__device__ __forceinline__ void solve_block4(const SpaceDev& sp, const SpaceDev* __restrict__ spaces, const SpaceCtx& c,
+                                             double* __restrict__ S, uint32_t hi, int lane)
+{
+    const int K = c.K;
+    const uint32_t s0 = (hi << 7) | ((uint32_t)lane << 2);
+    double* v = S + (ADJ ? sp.x_off : sp.y_off);
+    double acc[4], inv[4], r[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) acc[t] = ADJ ? rhs_adj(sp, spaces, S, s0 + t) : rhs_fwd(sp, spaces, S, s0 + t);
+    // bits >= 7: FWD visits the set bits of hi, ADJ the unset ones
+    uint32_t m = ADJ ? (~hi & ((1u << (K - 7)) - 1u)) : hi;
+    while (m) {
+        const int a = __ffs(m) + 6;
+        m &= m - 1;
+        const uint32_t bit = 1u << a;
+        const uint32_t p0 = ADJ ? s0 : (s0 ^ bit);
+        const double2* q = reinterpret_cast<const double2*>(v + (ADJ ? (s0 | bit) : p0));
+        rate4(c.bit[a], p0, r);
+        const double2 va = q[0], vb = q[1];
+        acc[0] = fma(r[0], va.x, acc[0]); acc[1] = fma(r[1], va.y, acc[1]);
+        acc[2] = fma(r[2], vb.x, acc[2]); acc[3] = fma(r[3], vb.y, acc[3]);
+    }
+    // diagonal
+    {
+        double dA[4], dB[4];
+        factor4(c.dA, 0, c.mA, s0, dA);
+        factor4(c.dB, (uint32_t)c.KA, c.mB, s0, dB);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) inv[t] = 1.0 / (dA[t] + dB[t]);
+    }
+    // edges inside the lane: bit 0 from t = 0 and t = 2, bit 1 from t = 0 and t = 1
+    rate4(c.bit[0], s0, r);
+    const double e0_0 = r[0], e0_2 = r[2];
+    rate4(c.bit[1], s0, r);
+    const double e1_0 = r[0], e1_1 = r[1];
+    // edges across lanes (bits 2..6): rate at the state that lacks the bit
+    double rl[5][4];
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+        const uint32_t bit = 4u << a;
+        const bool has = (s0 & bit) != 0;
+        if (ADJ ? !has : has) rate4(c.bit[a + 2], ADJ ? s0 : (s0 ^ bit), rl[a]);
+        else { rl[a][0] = 0.0; rl[a][1] = 0.0; rl[a][2] = 0.0; rl[a][3] = 0.0; }
+    }
+    const int pl = __popc(lane);
+    double val[4] = {0.0, 0.0, 0.0, 0.0};
+    if (!ADJ) {
+        for (int l = 0; l <= 5; ++l) {
+            const bool mine = pl == l;
+            if (mine) {
+                val[0] = acc[0] * inv[0];
+                val[1] = fma(e0_0, val[0], acc[1]) * inv[1];
+                val[2] = fma(e1_0, val[0], acc[2]) * inv[2];
+                val[3] = fma(e0_2, val[2], fma(e1_1, val[1], acc[3])) * inv[3];
+            }
+            if (l < 5) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const double pub = mine ? val[t] : 0.0;
+#pragma unroll
+                    for (int a = 0; a < 5; ++a) acc[t] = fma(rl[a][t], __shfl_xor_sync(0xffffffffu, pub, 1 << a), acc[t]);
+                }
+            }
+        }
+    } else {
+        for (int l = 5; l >= 0; --l) {
+            const bool mine = pl == l;
+            if (mine) {
+                val[3] = acc[3] * inv[3];
+                val[2] = fma(e0_2, val[3], acc[2]) * inv[2];
+                val[1] = fma(e1_1, val[3], acc[1]) * inv[1];
+                val[0] = fma(e0_0, val[1], fma(e1_0, val[2], acc[0])) * inv[0];
+            }
+            if (l > 0) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const double pub = mine ? val[t] : 0.0;
+#pragma unroll
+                    for (int a = 0; a < 5; ++a) acc[t] = fma(rl[a][t], __shfl_xor_sync(0xffffffffu, pub, 1 << a), acc[t]);
+                }
+            }
+        }
+    }
+    double2* o = reinterpret_cast<double2*>(v + s0);
+    o[0] = make_double2(val[0], val[1]);
+    o[1] = make_double2(val[2], val[3]);
+}
+
+template <bool ADJ>
+__global__ void __launch_bounds__(256)
+k_solve_small4(const SpaceDev* __restrict__ spaces, const uint32_t* __restrict__ list, uint32_t count, double* __restrict__ S)
+{
+    __shared__ SpaceCtx ctx[8];
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    if (w >= count) return;
+    const SpaceDev& sp = spaces[list[w]];
+    ctx_build(ctx[wl], sp, S, lane);
+    __syncwarp();
+    const uint32_t nblk = 1u << (sp.KA + sp.KB - 7);
+    if (!ADJ) {
+        for (uint32_t hi = 0; hi < nblk; ++hi) { solve_block4<false>(sp, spaces, ctx[wl], S, hi, lane); __syncwarp(); }
+    } else {
+        for (uint32_t hi = nblk; hi-- > 0;) { solve_block4<true>(sp, spaces, ctx[wl], S, hi, lane); __syncwarp(); }
+    }
+}
+
+template <bool ADJ>
+__global__ void __launch_bounds__(256)
+k_solve_big4(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs, const uint32_t* __restrict__ hs, double* __restrict__ S)
+{
+    __shared__ SpaceCtx ctx;
+    const Item sg = segs[blockIdx.x];
+    const SpaceDev& sp = spaces[sg.space];
+    ctx_build(ctx, sp, S, threadIdx.x);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (uint32_t r = w; r < sg.b; r += nw)
+        solve_block4<ADJ>(sp, spaces, ctx, S, hs[sg.a + r], lane);
+}
+
 // per-patient log-likelihood (likelihood.py:316,350,384,405,438)
 __global__ void k_logp(const SpaceDev* __restrict__ spaces, const uint32_t* __restrict__ list, uint32_t count,
                        const double* __restrict__ S, double* __restrict__ logp)
