@@ -523,18 +523,30 @@ __device__ __forceinline__ void solve_block4(const SpaceDev& sp, const SpaceDev*
     double acc[4], inv[4], r[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) acc[t] = ADJ ? rhs_adj(sp, spaces, S, s0 + t) : rhs_fwd(sp, spaces, S, s0 + t);
-    // bits >= 7: FWD visits the set bits of hi, ADJ the unset ones
+    // bits >= 7: FWD visits the set bits of hi, ADJ the unset ones; BATCH bits per round, loads before FMAs
     uint32_t m = ADJ ? (~hi & ((1u << (K - 7)) - 1u)) : hi;
+    constexpr int BATCH = 2;
     while (m) {
-        const int a = __ffs(m) + 6;
-        m &= m - 1;
-        const uint32_t bit = 1u << a;
-        const uint32_t p0 = ADJ ? s0 : (s0 ^ bit);
-        const double2* q = reinterpret_cast<const double2*>(v + (ADJ ? (s0 | bit) : p0));
-        rate4(c.bit[a], p0, r);
-        const double2 va = q[0], vb = q[1];
-        acc[0] = fma(r[0], va.x, acc[0]); acc[1] = fma(r[1], va.y, acc[1]);
-        acc[2] = fma(r[2], vb.x, acc[2]); acc[3] = fma(r[3], vb.y, acc[3]);
+        double rr[BATCH][4];
+        double2 va[BATCH], vb[BATCH];
+#pragma unroll
+        for (int q = 0; q < BATCH; ++q) {
+            // an exhausted slot re-reads the block's own (finished or not) location with rate 0
+            const bool on = m != 0;
+            const int a = on ? __ffs(m) + 6 : 7;
+            m &= m - 1;
+            const uint32_t bit = 1u << a;
+            const uint32_t p0 = ADJ ? s0 : (s0 ^ bit);
+            const double2* qv = reinterpret_cast<const double2*>(v + (on ? (ADJ ? (s0 | bit) : p0) : s0));
+            rate4(c.bit[a], on ? p0 : s0, rr[q]);
+            va[q] = qv[0]; vb[q] = qv[1];
+            if (!on) { rr[q][0] = 0.0; rr[q][1] = 0.0; rr[q][2] = 0.0; rr[q][3] = 0.0; va[q] = make_double2(0.0, 0.0); vb[q] = va[q]; }
+        }
+#pragma unroll
+        for (int q = 0; q < BATCH; ++q) {
+            acc[0] = fma(rr[q][0], va[q].x, acc[0]); acc[1] = fma(rr[q][1], va[q].y, acc[1]);
+            acc[2] = fma(rr[q][2], vb[q].x, acc[2]); acc[3] = fma(rr[q][3], vb[q].y, acc[3]);
+        }
     }
     // diagonal
     {
