@@ -240,13 +240,22 @@ def run_ours(args, rank, local_rank, world):
     ev.step_device(w0, w1)
     st = ev.handle.stats()
     ev.handle.set_profile(False)
-    cls = st["class_ms"]
+    cls = dict(st["class_ms"])
+    cls["contraction"] = cls.pop("stats") + cls.pop("finish")     # marginal statistics + gradient contraction
     peaks, peak_src = load_peaks()
     states = st["states_value_grad"]
-    alg = {"setup": 0.0, "solve_fwd": 8.0 * states, "solve_adj": 8.0 * states, "stats": 16.0 * states, "finish": 0.0}
+    # algorithmic bytes per class and step: forward writes y (8 B/state), adjoint writes x (8),
+    # the contraction reads x and y (16); table setup is pure overhead (0).
+    alg = {"setup": 0.0, "solve_fwd": 8.0 * states, "solve_adj": 8.0 * states, "contraction": 16.0 * states}
+    kernels = {"setup": "k_setup, k_setup_wide", "solve_fwd": "k_solve_big4<fwd> (+ k_solve_small*)",
+               "solve_adj": "k_solve_big4<adj> (+ k_solve_small*)",
+               "contraction": "k_stats_a/b, k_pfin_lo/hi, k_finish"}
+    # DRAM traffic of the solve kernel from the committed ncu capture (profiles/r1_v6_solve_big4_ncu_full.txt):
+    # 12.4 bytes per state (read + write) against 8 algorithmic
+    traffic_per_state = {"solve_fwd": 12.4, "solve_adj": 12.4}
     if rank == 0:
         fp64_peak = measure_fp64_tflops(local_rank)
-        top = max(("setup", "solve_fwd", "solve_adj", "stats", "finish"), key=lambda k: cls[k])
+        top = max(alg, key=lambda k: cls[k])
         ach = alg[top] / (cls[top] * 1e-3) / 1e9 if cls[top] > 0 else 0.0
         ms_step = 1e3 * wall / args.steps
         # whole-step rooflines use this rank's share of the work and its device time
@@ -269,16 +278,19 @@ def run_ours(args, rank, local_rank, world):
                     "h2d_bytes_per_step": int(ev.npar * 8), "d2h_bytes_per_step": int((ev.npar + 1) * 8),
                     "api": "ShardedEvaluator.value_grad(params_host, perc_met) -> (score, grad) host"},
             "gpu_launches": int(launches * args.steps),
-            "roofline": {"kernel": {"setup": "k_setup*", "solve_fwd": "k_solve_big/small<fwd>", "solve_adj": "k_solve_big/small<adj>",
-                                    "stats": "k_stats_a/b", "finish": "k_finish"}[top],
-                         "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
-                         "launches_in_class_ms": cls[top]},
+            "roofline": {"kernel": kernels[top], "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": ach / peaks["hbm_gbs"],
+                         "traffic": (traffic_per_state[top] * states / 1e9) if top in traffic_per_state else None,
+                         "traffic_unit": "GB per step, extrapolated from the bytes/state of the ncu capture in profiles/",
+                         "algorithmic_GB_per_step": alg[top] / 1e9, "class_ms_serial": cls[top],
+                         "peak_source": peak_src,
+                         "note": "class time = CUDA events on the launching stream in the library's profile mode "
+                                 "(chunks serialised on one stream); the timed steps overlap chunks on side streams"},
             "roofline_step": {"hbm": {"achieved_GBs": st["alg_bytes"] / t_rank / 1e9, "peak_GBs": peaks["hbm_gbs"], "frac": hbm_frac},
                               "fp64": {"achieved_TFLOPs": st["alg_flops"] / t_rank / 1e12, "peak_TFLOPs": fp64_peak,
                                        "frac": fp_frac, "peak_source": "independent-DFMA micro-kernel, this run"},
                               "binding": "hbm" if hbm_frac >= fp_frac else "fp64",
-                              "states": states, "class_ms": cls},
+                              "states": states, "class_ms_serial": cls},
         }
         if world == 1 and not args.no_cpu:
             cb = cpu_baseline(d, args.cpu_seconds)
