@@ -133,11 +133,10 @@ def learn_mhn(th_init, dp_init, dm_init, dat, perc_met: float, penal: Callable, 
     n_total = np.asarray(th_init).shape[0]
     x0 = _pack(th_init, dp_init, dm_init)
     options = {"maxiter": int(opt_iter), "ftol": opt_ftol}
-    try:
-        res = opt.minimize(fun=score_and_grad_reg, jac=True, x0=x0, method="L-BFGS-B",
-                           args=(h, perc_met, penal, w_penal), options=dict(options, disp=opt_v))
-    except (TypeError, ValueError):      # newer SciPy dropped the `disp` option of L-BFGS-B
-        res = opt.minimize(fun=score_and_grad_reg, jac=True, x0=x0, method="L-BFGS-B",
-                           args=(h, perc_met, penal, w_penal), options=options)
+    import scipy
+    if tuple(int(v) for v in scipy.__version__.split(".")[:2]) < (1, 15):
+        options["disp"] = opt_v           # SciPy >= 1.15 rewrote L-BFGS-B and no longer takes `disp`
+    res = opt.minimize(fun=score_and_grad_reg, jac=True, x0=x0, method="L-BFGS-B",
+                       args=(h, perc_met, penal, w_penal), options=options)
     th, dp, dm = _unpack(res.x, n_total)
     return th.copy(), dp.copy(), dm.copy()

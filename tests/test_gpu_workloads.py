@@ -1,0 +1,78 @@
+"""GPU tests on the reference's own workload (LUAD, 28 events) and of the optimiser loop."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL = 1e-10
+
+
+def test_luad_subset_against_reference_golden():
+    import metmhn_b200 as mm
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_luad.npz"))
+    s, gg, a, b = mm.score_and_grad(g["theta"], g["d_p"], g["d_m"], g["rows"], 0.65)
+    assert abs(s - g["score"]) <= TOL * abs(g["score"])
+    assert rel_err(gg, g["g"]) <= TOL and rel_err(a, g["gdp"]) <= TOL and rel_err(b, g["gdm"]) <= TOL
+    assert abs(mm.score(g["theta"], g["d_p"], g["d_m"], g["rows"], 0.65) - g["score_only"]) <= TOL * abs(g["score"])
+
+
+def test_full_luad_properties():
+    """Whole LUAD dataset (4852 rows, paired lattices up to 2^21): size-independent checks.
+    (1) the dataset score is the weighted mean of the per-row log-likelihoods (regularized_optimization.py:256-263);
+    (2) a shard-wise evaluation with global weights adds up to the full result (linearity);
+    (3) the gradient is the derivative: directional finite difference of the score."""
+    from metmhn_b200 import Handle
+    from metmhn_b200.sharded import class_weights, partition
+    from metmhn_b200.utility import indep
+    dat = np.load(os.path.join(ROOT, "tests", "golden", "luad_dat.npz"))["dat"]
+    th, dp, dm = indep(dat)
+    rng = np.random.default_rng(5)
+    p = np.concatenate([th.ravel(), dp, dm]) + rng.normal(0, 0.05, 29 * 31)
+    h = Handle(dat)
+    s, g = h.value_grad(p, 0.65)
+    lp = h.per_patient(p)
+    w0, w1 = class_weights(dat.shape[0], float(dat[:, -3].astype(np.int64).sum()), 0.65)
+    w = np.where(dat[:, -1] == 0, w0, w1)
+    assert abs((w * lp).sum() - s) <= 1e-12 * abs(s)
+    assert np.isfinite(g).all()
+    a = partition(dat, 2)
+    tot = np.zeros(1 + p.shape[0])
+    for r in range(2):
+        hs = Handle(np.ascontiguousarray(dat[a == r]))
+        sr, gr = hs.eval_weighted(p, w0, w1)
+        tot[0] += sr
+        tot[1:] += gr
+        hs.close()
+    assert abs(tot[0] - s) <= 1e-12 * abs(s) and rel_err(tot[1:], g) <= 1e-10
+    d = rng.normal(0, 1, p.shape[0])
+    d /= np.linalg.norm(d)
+    eps = 1e-6
+    fd = (h.value(p + eps * d, 0.65) - h.value(p - eps * d, 0.65)) / (2 * eps)
+    assert abs(fd - g @ d) <= 1e-6 * max(1.0, abs(g @ d))
+
+
+def test_learn_mhn_converges_and_matches_oracle_objective():
+    """L-BFGS-B on the GPU objective (reference: regularized_optimization.py:301-334).  Optimiser-trajectory parity
+    is unpinned (SciPy version differs from the reference's pin); we check the optimum instead: the objective
+    decreases, the projected gradient is small, and the CPU oracle agrees on objective and gradient there."""
+    import metmhn_b200 as mm
+    from metmhn_b200.simulate import syn_v1
+    from metmhn_b200.utility import indep
+    from oracle import reference_restated as rr
+    d = syn_v1(6, 300, 606, max_joint_bits=11)
+    dat = d["dat"]
+    th0, dp0, dm0 = indep(dat)
+    lam = 1e-3
+    x0 = np.concatenate([th0.ravel(), dp0, dm0])
+    f0, _ = mm.score_and_grad_reg(x0, dat, 0.65, mm.symmetric_penal, lam)
+    th, dp, dm = mm.learn_mhn(th0, dp0, dm0, dat, 0.65, mm.symmetric_penal, lam, opt_ftol=1e-9, opt_v=False)
+    x = np.concatenate([th.ravel(), dp, dm])
+    f, g = mm.score_and_grad_reg(x, dat, 0.65, mm.symmetric_penal, lam)
+    assert float(f) < float(f0) - 1e-3
+    assert np.abs(g).max() < 5e-3
+    f_ref, g_ref = rr.score_and_grad_reg(x, dat, 0.65, rr.symmetric_penal, lam)
+    assert abs(float(f) - f_ref) <= 1e-10 * abs(f_ref) and rel_err(g, g_ref) <= 1e-8
