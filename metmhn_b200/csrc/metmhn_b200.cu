@@ -94,13 +94,17 @@ static uint64_t space_scratch(SpaceDev& s, uint64_t off)
     s.tabB = s.kind == K_JOINT ? table(s.KB, s.splitB) : 0;
     s.y_off = take(N);
     s.x_off = take(N);
-    s.stA = s.stB = s.stP = 0;
-    s.slices = 1;
+    s.stA = s.stB = s.stP = s.stPB = 0;
+    s.slices = 1; s.slicesB = 1;
     if (s.kind == K_JOINT) {
-        s.slices = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(1, NB / 64));
+        // group-A statistics sum over uB, group-B statistics over uA: slice the summed range so that lopsided pairs
+        // (one tumour with many events, the other with few) still expose enough parallel work
+        s.slices = (uint32_t)std::min<uint64_t>(256, std::max<uint64_t>(1, NB / 128));
+        s.slicesB = (uint32_t)std::min<uint64_t>(256, std::max<uint64_t>(1, NA / 2048));
         s.stA = take((s.KA + 1) * NA);
         s.stB = take((s.KB + 1) * NB);
         s.stP = take((uint64_t)s.slices * (s.KA + 1) * NA);
+        s.stPB = take((uint64_t)s.slicesB * (s.KB + 1) * NB);
     } else if (s.kind != K_PRE && s.splitA) {
         // product-form gradient: weighted marginals over the low / high part (k_pfin_lo / k_pfin_hi)
         const uint64_t N1 = 1ull << s.splitA, N2 = 1ull << (s.KA - s.splitA);
@@ -270,7 +274,7 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
             const uint32_t base_idx = (uint32_t)(spaces.size() - ck.space0);
             for (SpaceDev s : pp.sp) {
                 s.y_off += used; s.x_off += used; s.tabA += used;
-                if (s.kind == K_JOINT) { s.tabB += used; s.stA += used; s.stB += used; s.stP += used; }
+                if (s.kind == K_JOINT) { s.tabB += used; s.stA += used; s.stB += used; s.stP += used; s.stPB += used; }
                 else if (s.stP) s.stP += used;                  // product-form single-tumour spaces
                 if (s.joint >= 0) s.joint += base_idx;
                 if (s.pre >= 0) s.pre += base_idx;
@@ -353,15 +357,18 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
         ck.st_a.cnt = (uint32_t)(items.size() - ck.st_a.off);
         ck.st_ar.off = items.size();
         for (uint32_t i = 0; i < ck.nspaces; ++i)
-            if (sp[i].kind == K_JOINT) {
-                const uint64_t len = (uint64_t)(sp[i].KA + 1) << sp[i].KA;
-                for (uint64_t t = 0; t < len; t += 1024) items.push_back({i, 0u, (uint32_t)(t / 1024)});
-            }
+            if (sp[i].kind == K_JOINT)
+                for (uint32_t g = 0; g < 2; ++g) {
+                    const int KG = g ? sp[i].KB : sp[i].KA;
+                    const uint64_t len = (uint64_t)(KG + 1) << KG;
+                    for (uint64_t t = 0; t < len; t += 1024) items.push_back({i, g, (uint32_t)(t / 1024)});
+                }
         ck.st_ar.cnt = (uint32_t)(items.size() - ck.st_ar.off);
         ck.st_b.off = items.size();
         for (uint32_t i = 0; i < ck.nspaces; ++i)
             if (sp[i].kind == K_JOINT)
-                for (uint32_t u = 0; u < (1u << sp[i].KB); u += 8) items.push_back({i, u, std::min<uint32_t>(8u, (1u << sp[i].KB) - u)});
+                for (uint32_t sl = 0; sl < sp[i].slicesB; ++sl)
+                    for (uint32_t u = 0; u < (1u << sp[i].KB); ++u) items.push_back({i, u, sl});
         ck.st_b.cnt = (uint32_t)(items.size() - ck.st_b.off);
         auto is_prod = [](const SpaceDev& s) { return s.kind != K_JOINT && s.kind != K_PRE && s.splitA; };
         ck.pf_lo.off = items.size();
@@ -533,8 +540,8 @@ static int run_eval(mmh_handle* h, const double* d_params, double w0, double w1,
         tick(3);
         if (ck.st_a.cnt) {
             k_stats_a<<<(ck.st_a.cnt + 7) / 8, 256, 0, st>>>(sp, h->d_items + ck.st_a.off, ck.st_a.cnt, S);
-            k_stats_a_reduce<<<ck.st_ar.cnt, 1024, 0, st>>>(sp, h->d_items + ck.st_ar.off, S);
-            k_stats_b<<<ck.st_b.cnt, 256, 0, st>>>(sp, h->d_items + ck.st_b.off, S);
+            k_stats_b<<<(ck.st_b.cnt + 7) / 8, 256, 0, st>>>(sp, h->d_items + ck.st_b.off, ck.st_b.cnt, S);
+            k_stats_reduce<<<ck.st_ar.cnt, 1024, 0, st>>>(sp, h->d_items + ck.st_ar.off, S);
             launches += 3;
         }
         tick(4);

@@ -36,6 +36,8 @@ struct SpaceDev {
     uint32_t slices;                 // joint only: partial-sum slices of the group-A statistics
     uint8_t  splitA, splitB;         // 0, or the number of low bits held by the first of two product tables
     uint8_t  pad[2];
+    uint32_t slicesB, pad2;          // joint only: partial-sum slices of the group-B statistics
+    uint64_t stPB;                   // joint only: group-B partials (slicesB x (KB+1) x NB)
     uint64_t y_off, x_off;           // scratch offsets (in doubles)
     uint64_t tabA, tabB;             // NR x NA and NR x NB rate / diagonal tables
     uint64_t stA, stB, stP;          // joint only: marginal statistics ((KA+1) x NA, (KB+1) x NB, partials)
@@ -775,28 +777,31 @@ k_stats_a(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, u
     }
 }
 
-__global__ void k_stats_a_reduce(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items,
-                                 double* __restrict__ S)
+__global__ void k_stats_reduce(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items,
+                               double* __restrict__ S)
 {
-    const Item it = items[blockIdx.x];               // b = first element of a 1024-element block (in units of 1024)
+    const Item it = items[blockIdx.x];               // a = group, b = first element of a 1024-element block (units of 1024)
     const SpaceDev& sp = spaces[it.space];
-    const uint64_t len = (uint64_t)(sp.KA + 1) << sp.KA;
+    const int KG = it.a ? sp.KB : sp.KA;
+    const uint64_t len = (uint64_t)(KG + 1) << KG;
     const uint64_t t = (uint64_t)it.b * 1024u + threadIdx.x;
     if (t >= len) return;
+    const uint32_t ns = it.a ? sp.slicesB : sp.slices;
+    const double* src = S + (it.a ? sp.stPB : sp.stP);
     double s = 0.0;
-    for (uint32_t k = 0; k < sp.slices; ++k) s += S[sp.stP + k * len + t];
-    S[sp.stA + t] = s;
+    for (uint32_t k = 0; k < ns; ++k) s += src[k * len + t];
+    S[(it.a ? sp.stB : sp.stA) + t] = s;
 }
 
 // group-B statistics: one warp per uB; dot products of the y row with the x rows of up to four free bits at a
 // time, 16-byte loads.
-__device__ __forceinline__ void row_dots4(const double* __restrict__ yr, const double* const (&xr)[4], uint32_t NA, int lane,
-                                          double (&acc)[4])
+__device__ __forceinline__ void row_dots4(const double* __restrict__ yr, const double* const (&xr)[4], uint32_t NA,
+                                          uint32_t i0, uint32_t i1, int lane, double (&acc)[4])
 {
 #pragma unroll
     for (int q = 0; q < 4; ++q) acc[q] = 0.0;
     if (NA >= 2) {
-        for (uint32_t i = 2 * lane; i < NA; i += 64) {
+        for (uint32_t i = i0 + 2 * lane; i < i1; i += 64) {
             const double2 yv = *reinterpret_cast<const double2*>(yr + i);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -813,18 +818,21 @@ __device__ __forceinline__ void row_dots4(const double* __restrict__ yr, const d
 }
 
 __global__ void __launch_bounds__(256)
-k_stats_b(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, double* __restrict__ S)
+k_stats_b(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, uint32_t count, double* __restrict__ S)
 {
-    const Item it = items[blockIdx.x];               // a = first uB, b = count (one warp each)
+    const uint32_t wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wg >= count) return;
+    const Item it = items[wg];                       // a = uB, b = slice of the uA range (one warp per item)
     const SpaceDev& sp = spaces[it.space];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if ((uint32_t)w >= it.b) return;
     const int KA = sp.KA, KB = sp.KB;
     const uint32_t NA = 1u << KA, NB = 1u << KB;
-    const uint32_t uB = it.a + w;
+    const uint32_t uB = it.a;
+    const uint32_t per = ((NA + sp.slicesB - 1) / sp.slicesB + 63u) & ~63u;
+    const uint32_t i0 = min(NA, it.b * per), i1 = min(NA, i0 + per);
     const double* yr = S + sp.y_off + ((uint64_t)uB << KA);
     const double* xb = S + sp.x_off;
-    double* out = S + sp.stB;
+    double* out = S + sp.stPB + (uint64_t)it.b * (KB + 1) * NB;
     // row 0 (g = sum x y) travels with the first group of free bits
     int rows[4] = {0, -1, -1, -1};
     int nrow = 1;
@@ -842,7 +850,7 @@ k_stats_b(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, d
                 xr[q] = xb + ((uint64_t)(r == 0 ? uB : (uB | (1u << (r - 1)))) << KA);
             }
             double acc[4];
-            row_dots4(yr, xr, NA, lane, acc);
+            row_dots4(yr, xr, NA, i0, i1, lane, acc);
             if (lane == 0)
 #pragma unroll
                 for (int q = 0; q < 4; ++q) if (q < nrow) out[(uint64_t)rows[q] * NB + uB] = acc[q];
