@@ -241,7 +241,8 @@ def run_ours(args, rank, local_rank, world):
     st = ev.handle.stats()
     ev.handle.set_profile(False)
     cls = dict(st["class_ms"])
-    cls["contraction"] = cls.pop("stats") + cls.pop("finish")     # marginal statistics + gradient contraction
+    detail = dict(cls)
+    cls["contraction"] = cls.pop("stats") + cls.pop("finish") + cls.pop("pfin")     # marginal statistics + gradient contraction
     peaks, peak_src = load_peaks()
     states = st["states_value_grad"]
     # algorithmic bytes per class and step: forward writes y (8 B/state), adjoint writes x (8),
@@ -290,7 +291,7 @@ def run_ours(args, rank, local_rank, world):
                               "fp64": {"achieved_TFLOPs": st["alg_flops"] / t_rank / 1e12, "peak_TFLOPs": fp64_peak,
                                        "frac": fp_frac, "peak_source": "independent-DFMA micro-kernel, this run"},
                               "binding": "hbm" if hbm_frac >= fp_frac else "fp64",
-                              "states": states, "class_ms_serial": cls},
+                              "states": states, "class_ms_serial": cls, "class_ms_detail": detail},
         }
         if world == 1 and not args.no_cpu:
             cb = cpu_baseline(d, args.cpu_seconds)

@@ -56,7 +56,7 @@ typedef struct mmh_stats_t {
     int64_t k_hist[4][64];    /* [type][k] histogram of restricted sizes */
     double  class_ms[8];      /* profile mode: device ms by kernel class of the last evaluation:
                                  0 table setup, 1 forward solves, 2 adjoint solves, 3 marginal statistics,
-                                 4 gradient contraction, 5 other */
+                                 4 gradient contraction (k_finish), 5 other, 6 weighted marginals of product-form spaces */
 } mmh_stats_t;
 
 /* Copy + preprocess the dataset (parse rows, canonical bit layout, bucket by lattice size,

@@ -142,7 +142,7 @@ class Handle:
         s = Stats()
         check(lib().mmh_stats(self._h, C.byref(s)))
         d = {k: getattr(s, k) for k, _ in Stats._fields_ if k not in ("k_hist", "class_ms")}
-        d["class_ms"] = dict(zip(("setup", "solve_fwd", "solve_adj", "stats", "finish", "other"), list(s.class_ms)[:6]))
+        d["class_ms"] = dict(zip(("setup", "solve_fwd", "solve_adj", "stats", "finish", "other", "pfin"), list(s.class_ms)[:7]))
         d["k_hist"] = {t: {k: int(s.k_hist[t][k]) for k in range(64) if s.k_hist[t][k]} for t in range(4)}
         return d
 

@@ -14,6 +14,8 @@
 
 using namespace mmh;
 
+static constexpr size_t FIN_SMEM = (size_t)(NACC * NR * NR + FIN_WARPS * NR * 33) * sizeof(double);
+
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
@@ -440,8 +442,8 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
-    CK(cudaFuncSetAttribute(k_finish<MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * NACC * NR * NR * (int)sizeof(double)));
-    CK(cudaFuncSetAttribute(k_finish<MAXG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * NACC * NR * NR * (int)sizeof(double)));
+    CK(cudaFuncSetAttribute(k_finish<MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIN_SMEM));
+    CK(cudaFuncSetAttribute(k_finish<MAXG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIN_SMEM));
     h->st.scratch_bytes = (double)max_scratch * 8.0 * h->ns;
     *out = h;
     return MMH_OK;
@@ -544,7 +546,7 @@ static int run_eval(mmh_handle* h, const double* d_params, double w0, double w1,
             k_stats_reduce<<<ck.st_ar.cnt, 1024, 0, st>>>(sp, h->d_items + ck.st_ar.off, S);
             launches += 3;
         }
-        tick(4);
+        tick(6);
         if (ck.pf_lo.cnt) {
             if (ck.wide) {
                 k_pfin_lo<MAXG><<<(ck.pf_lo.cnt + 7) / 8, 256, 0, st>>>(sp, h->d_items + ck.pf_lo.off, ck.pf_lo.cnt, S);
@@ -555,9 +557,11 @@ static int run_eval(mmh_handle* h, const double* d_params, double w0, double w1,
             }
             launches += 2;
         }
-        const size_t fin_smem = 4 * NACC * NR * NR * sizeof(double);
-        if (ck.wide) k_finish<MAXG><<<h->fin_ctas, 128, fin_smem, st>>>(sp, h->d_items + ck.fin.off, ck.fin.cnt, S, w0, w1, d_partial);
-        else         k_finish<MAXT><<<h->fin_ctas, 128, fin_smem, st>>>(sp, h->d_items + ck.fin.off, ck.fin.cnt, S, w0, w1, d_partial);
+        tick(4);
+        const size_t fin_smem = FIN_SMEM;
+        const int fin_grid = (int)std::max<uint32_t>(1u, std::min<uint32_t>((uint32_t)h->fin_ctas, (ck.fin.cnt + 2 * FIN_WARPS - 1) / (2 * FIN_WARPS)));
+        if (ck.wide) k_finish<MAXG><<<fin_grid, FIN_WARPS * 32, fin_smem, st>>>(sp, h->d_items + ck.fin.off, ck.fin.cnt, S, w0, w1, d_partial);
+        else         k_finish<MAXT><<<fin_grid, FIN_WARPS * 32, fin_smem, st>>>(sp, h->d_items + ck.fin.off, ck.fin.cnt, S, w0, w1, d_partial);
         ++launches;
     }
     st = main_stream;

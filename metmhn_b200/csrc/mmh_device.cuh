@@ -23,7 +23,7 @@ constexpr int MAXT    = 16;   // bits per group with one explicit table; wider g
 constexpr int MAXG    = 26;   // bits per group
 constexpr int BIGK    = 13;   // spaces with K >= BIGK are solved by per-level launches
 constexpr int SEGB    = 32;   // blocks of 32 states per big-tier segment (one CTA)
-constexpr int FIN_U   = 64;   // sub-states per finish work item
+constexpr int FIN_U   = 256;  // sub-states per finish work item
 
 enum Kind : uint8_t { K_PRE = 0, K_JOINT = 1, K_PF = 2, K_MF = 3, K_S1 = 4, K_S2 = 5 };
 
@@ -967,126 +967,147 @@ k_pfin_hi(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, d
 }
 
 // ------------------------------------------------------------------------------------------
-// Gradient contraction.  lane = table row (event i, or one of the two diagnosis pseudo rows); the warp
-// walks FIN_U sub-states of one group.  For event i not in sub-state u
+// Gradient contraction.  For event row i and sub-state u of a group (i not in u)
 //     w_i(u) = T[i][u] * E_i(u),   E_i(u) = sum_other y (x[u + i] - x[u])   (i is a bit of the group)
 //                                          = - sum_other x y                (i absent in this patient)
 // and  dL/dlogW[i][ev(b)] += w_i(u) for every bit b of u,  dL/dlogW[i][i] += w_i(u)
 // (likelihood.py:125-201 and vanilla.py:328-393 do this with one shuffle pass per (i, j)).
-// Accumulation is per warp in shared memory, rows are lane-private: no atomics, fixed order.
+// A warp takes FIN_U sub-states of one group, 32 at a time:
+//   phase 1, lane = sub-state: w_r(u) for every row r with coalesced table / statistics reads -> shared tile
+//   phase 2, lane = row: the 32 values of the row are folded into per-bit sums; the membership of the five low
+//            bits is known at compile time, the higher bits are uniform over the tile.
+// The per-item results go into one shared accumulator per CTA in a fixed warp order (no atomics): repeated
+// evaluations are bit-identical.
 constexpr int NACC = 3;                               // effective-parameter spaces: theta, theta_pt/d_p, theta/d_m
+constexpr int FIN_WARPS = 4;
 template <int MB>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(FIN_WARPS * 32)
 k_finish(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, uint32_t count,
          const double* __restrict__ S, double w_type0, double w_other, double* __restrict__ partial)
 {
-    extern __shared__ double sm[];                    // [warps][NACC][NR][NR]
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    double* G = sm + (size_t)w * NACC * NR * NR;
-    for (int t = lane; t < NACC * NR * NR; t += 32) G[t] = 0.0;
-    __syncwarp();
-    const uint32_t gw = blockIdx.x * nw + w, gn = gridDim.x * nw;
-    const uint32_t per = (count + gn - 1) / gn;
-    const uint32_t i0 = gw * per, i1 = min(count, i0 + per);
-    for (uint32_t k = i0; k < i1; ++k) {
-        const Item it = items[k];                     // a = group, b = first sub-state
-        const SpaceDev& sp = spaces[it.space];
-        const int pmode = it.a >= 2 ? (int)it.a - 1 : 0;     // 0 table mode, 1 product low part, 2 product high part
-        const int g = pmode ? 0 : (int)it.a;
-        const bool joint = sp.kind == K_JOINT;
-        const int K1 = sp.splitA;
-        const int KG = pmode == 1 ? K1 : pmode == 2 ? sp.KA - K1 : (g ? sp.KB : sp.KA);
-        const uint32_t NG = 1u << KG;
-        const uint8_t* ev = (g ? sp.evB : sp.evA) + (pmode == 2 ? K1 : 0);
-        const Side sd = side_of(sp, g, S);
-        const double* ptab = pmode == 2 ? sd.t + ((uint64_t)NR << K1) : sd.t;     // T1 or T2
-        const double* pH = S + sp.stP + (pmode == 2 ? (uint64_t)sp.slices * (NR + sp.KA) * (1u << K1) : 0);
-        const int psl = pmode == 1 ? (int)sp.slices : 1;
-        const double* st = S + (g ? sp.stB : sp.stA);
-        const double* y = S + sp.y_off;
-        const double* x = S + sp.x_off;
-        const int n_tot = sp.n_tot, n = n_tot - 1;
-        int nrows = n, accid = 0;
-        bool always_n = false, pseudo_tot = false;
-        switch (sp.kind) {
-            case K_PRE:   nrows = n_tot; accid = 0; break;
-            case K_JOINT: nrows = n; accid = 0; always_n = (g == 1); pseudo_tot = true; break;
-            case K_PF:    nrows = n; accid = 2; always_n = true; break;
-            case K_MF:    nrows = n; accid = 1; always_n = true; break;
-            case K_S1:    nrows = n_tot; accid = 1; break;
-            default:      nrows = n_tot; accid = 0; break;
-        }
-        const bool is_row = lane < nrows;
-        const bool is_pseudo = (lane == ROW_DP || lane == ROW_DM) &&
-                               (sp.kind == K_PRE || sp.kind == K_JOINT || sp.kind == K_S2);
-        int abit = -1, abit_full = -1;                       // bit of this lane's event in the group / in the space
-        for (int b = 0; b < KG; ++b) if (ev[b] == lane) abit = b;
-        if (pmode) for (int b = 0; b < sp.KA; ++b) if (sp.evA[b] == lane) abit_full = b;
-        const double wgt = sp.cls ? w_other : w_type0;
+    extern __shared__ double sm[];                    // [NACC][NR][NR] accumulator, then FIN_WARPS tiles of 32 x 33
+    double* G = sm;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double* tile = sm + NACC * NR * NR + w * (NR * 33);
+    for (int t = threadIdx.x; t < NACC * NR * NR; t += blockDim.x) G[t] = 0.0;
+    __syncthreads();
+    const uint32_t per_cta = (count + gridDim.x - 1) / gridDim.x;
+    const uint32_t c0 = blockIdx.x * per_cta, c1 = min(count, c0 + per_cta);
+    for (uint32_t base = c0; base < c1; base += FIN_WARPS) {
+        const uint32_t k = base + w;
+        const bool have = k < c1;
         double tot = 0.0, ac[MB];
 #pragma unroll
         for (int b = 0; b < MB; ++b) ac[b] = 0.0;
-        const uint32_t u1 = min(NG, it.b + FIN_U);
-        for (uint32_t u = it.b; u < u1; ++u) {
-            double wv = 0.0;
-            if (pmode) {
-                if (is_row || is_pseudo) {
-                    double hsum = 0.0, csum = 0.0;
-                    const uint64_t slice = (uint64_t)(NR + sp.KA) * NG;
-                    for (int q = 0; q < psl; ++q) {
-                        hsum += pH[q * slice + (uint64_t)lane * NG + u];
-                        if (is_row && abit_full >= 0) csum += pH[q * slice + (uint64_t)(NR + abit_full) * NG + u];
+        int KG = 0, accid = 0, n = 0, pmode = 0;
+        bool always_n = false, pseudo_tot = false, is_row = false, is_pseudo = false;
+        const uint8_t* ev = nullptr;
+        double wgt = 0.0;
+        if (have) {
+            const Item it = items[k];                 // a = group (0/1) or 2/3 = product low/high part, b = first sub-state
+            const SpaceDev& sp = spaces[it.space];
+            pmode = it.a >= 2 ? (int)it.a - 1 : 0;
+            const int g = pmode ? 0 : (int)it.a;
+            const bool joint = sp.kind == K_JOINT;
+            const int K1 = sp.splitA;
+            KG = pmode == 1 ? K1 : pmode == 2 ? sp.KA - K1 : (g ? sp.KB : sp.KA);
+            const uint32_t NG = 1u << KG;
+            ev = (g ? sp.evB : sp.evA) + (pmode == 2 ? K1 : 0);
+            const Side sd = side_of(sp, g, S);
+            const double* ptab = pmode == 2 ? sd.t + ((uint64_t)NR << K1) : sd.t;     // T1 or T2
+            const double* pH = S + sp.stP + (pmode == 2 ? (uint64_t)sp.slices * (NR + sp.KA) * (1u << K1) : 0);
+            const int psl = pmode == 1 ? (int)sp.slices : 1;
+            const uint64_t pslice = (uint64_t)(NR + sp.KA) * NG;
+            const double* st = S + (g ? sp.stB : sp.stA);
+            const double* y = S + sp.y_off;
+            const double* x = S + sp.x_off;
+            const int n_tot = sp.n_tot;
+            n = n_tot - 1;
+            int nrows = n;
+            switch (sp.kind) {
+                case K_PRE:   nrows = n_tot; accid = 0; break;
+                case K_JOINT: nrows = n; accid = 0; always_n = (g == 1); pseudo_tot = true; break;
+                case K_PF:    nrows = n; accid = 2; always_n = true; break;
+                case K_MF:    nrows = n; accid = 1; always_n = true; break;
+                case K_S1:    nrows = n_tot; accid = 1; break;
+                default:      nrows = n_tot; accid = 0; break;
+            }
+            const bool has_pseudo = (sp.kind == K_PRE || sp.kind == K_JOINT || sp.kind == K_S2);
+            is_row = lane < nrows;
+            is_pseudo = (lane == ROW_DP || lane == ROW_DM) && has_pseudo;
+            wgt = sp.cls ? w_other : w_type0;
+            // bit of row `lane` inside the group (table mode) / inside the whole space (product mode)
+            int abit = -1;
+            if (pmode) { for (int b = 0; b < sp.KA; ++b) if (sp.evA[b] == lane) abit = b; }
+            else       { for (int b = 0; b < KG; ++b) if (ev[b] == lane) abit = b; }
+            const bool pre_seed = sp.kind == K_PRE;
+            const SpaceDev& jsp = spaces[pre_seed ? sp.joint : it.space];
+            const uint32_t u_end = min(NG, it.b + FIN_U);
+            for (uint32_t u0 = it.b; u0 < u_end; u0 += 32) {
+                const uint32_t u = u0 + lane;
+                const bool uv = u < u_end;
+                // ---- phase 1: lane = sub-state ----
+                double gg = 0.0, xv = 0.0, yv = 0.0;
+                if (uv && !pmode) { if (joint) gg = st[u]; else { xv = x[u]; yv = y[u]; gg = xv * yv; } }
+                for (int r = 0; r < NR; ++r) {
+                    const int rb = __shfl_sync(0xffffffffu, abit, r);
+                    const bool rrow = r < nrows, rps = (r == ROW_DP || r == ROW_DM) && has_pseudo;
+                    double wv = 0.0;
+                    if (uv && (rrow || rps)) {
+                        if (pmode) {
+                            double hsum = 0.0, csum = 0.0;
+                            for (int q = 0; q < psl; ++q) {
+                                hsum += pH[q * pslice + (uint64_t)r * NG + u];
+                                if (rrow && rb >= 0) csum += pH[q * pslice + (uint64_t)(NR + rb) * NG + u];
+                            }
+                            wv = ptab[(uint64_t)r * NG + u] * (csum - hsum);
+                        } else {
+                            const double R = rrow ? sd.rate(r, u) : sd.special(r, u);
+                            double E = -gg;
+                            if (rrow && rb >= 0) {
+                                if ((u >> rb) & 1u) E = 0.0;
+                                else if (joint) E = st[(uint64_t)(1 + rb) * NG + u] - gg;
+                                else E = yv * (x[u | (1u << rb)] - xv);
+                            }
+                            wv = R * E;
+                            // the seeding edge of the pre-seeding lattice ends in the joint lattice
+                            if (pre_seed && r == n) wv += R * yv * S[jsp.x_off + (((uint64_t)u << jsp.KA) | u)];
+                        }
                     }
-                    wv = ptab[(uint64_t)lane * NG + u] * (csum - hsum);
+                    tile[r * 33 + lane] = wv;
                 }
-            } else if (is_row || is_pseudo) {
-                const double R = is_row ? sd.rate(lane, u) : sd.special(lane, u);
-                double E;
-                if (joint) {
-                    const double gg = st[u];
-                    if (is_row && abit >= 0) E = ((u >> abit) & 1u) ? 0.0 : st[(uint64_t)(1 + abit) * NG + u] - gg;
-                    else E = -gg;
-                } else {
-                    const double xv = x[u], yv = y[u];
-                    if (is_row && abit >= 0) E = ((u >> abit) & 1u) ? 0.0 : yv * (x[u | (1u << abit)] - xv);
-                    else E = -xv * yv;
+                __syncwarp();
+                // ---- phase 2: lane = row ----
+                double tsum = 0.0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const double wv = tile[lane * 33 + j];
+                    tsum += wv;
+#pragma unroll
+                    for (int b = 0; b < 5; ++b) if ((j >> b) & 1) ac[b] += wv;
                 }
-                wv = R * E;
-            }
-            tot += wv;
+                tot += tsum;
 #pragma unroll
-            for (int b = 0; b < MB; ++b) if (b < KG && ((u >> b) & 1u)) ac[b] += wv;
-        }
-        // the seeding edge of the pre-seeding lattice ends in the joint lattice (row n of K_PRE)
-        if (sp.kind == K_PRE && lane == n) {
-            // E used x0[u|bit] semantics above with abit = -1  ->  -x0 y0 ; add the missing + y0 * x_joint[embed(u)]
-            const SpaceDev& j = spaces[sp.joint];
-            const double* xj = S + j.x_off;
-            for (uint32_t u = it.b; u < u1; ++u) {
-                const double wv = sd.rate(n, u) * y[u] * xj[((uint64_t)u << j.KA) | u];
-                tot += wv;
-#pragma unroll
-                for (int b = 0; b < MB; ++b) if (b < KG && ((u >> b) & 1u)) ac[b] += wv;
+                for (int b = 5; b < MB; ++b) if (b < KG && ((u0 >> b) & 1u)) ac[b] += tsum;
+                __syncwarp();
             }
         }
-        if (is_row || is_pseudo) {
-            double* row = G + ((size_t)accid * NR + lane) * NR;
+        // ---- flush into the CTA accumulator, warp after warp ----
+        for (int q = 0; q < FIN_WARPS; ++q) {
+            if (q == w && have && (is_row || is_pseudo)) {
+                double* row = G + ((size_t)accid * NR + lane) * NR;
 #pragma unroll
-            for (int b = 0; b < MB; ++b) if (b < KG) row[ev[b]] += wgt * ac[b];
-            if (pmode != 2) {                                   // totals are counted once (low part)
-                if (is_row) { row[lane] += wgt * tot; if (always_n) row[n] += wgt * tot; }
-                else if (pseudo_tot) row[n] += wgt * tot;
+                for (int b = 0; b < MB; ++b) if (b < KG) row[ev[b]] += wgt * ac[b];
+                if (pmode != 2) {                               // totals are counted once (low part)
+                    if (is_row) { row[lane] += wgt * tot; if (always_n) row[n] += wgt * tot; }
+                    else if (pseudo_tot) row[n] += wgt * tot;
+                }
             }
+            __syncthreads();
         }
-        __syncwarp();
     }
-    __syncthreads();
     double* out = partial + (size_t)blockIdx.x * NACC * NR * NR;
-    for (int t = threadIdx.x; t < NACC * NR * NR; t += blockDim.x) {
-        double s = 0.0;
-        for (int k = 0; k < nw; ++k) s += sm[(size_t)k * NACC * NR * NR + t];
-        out[t] += s;                                   // same CTA index, chunk after chunk: fixed order
-    }
+    for (int t = threadIdx.x; t < NACC * NR * NR; t += blockDim.x) out[t] += G[t];     // same CTA index, chunk after chunk
 }
 
 // ------------------------------------------------------------------------------------------
