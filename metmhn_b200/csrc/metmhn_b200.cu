@@ -385,7 +385,7 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
         for (uint32_t i = 0; i < ck.nspaces; ++i)
             if (is_prod(sp[i])) {
                 const uint32_t N2 = 1u << (sp[i].KA - sp[i].splitA);
-                for (uint32_t u = 0; u < N2; u += 8) items.push_back({i, u, std::min<uint32_t>(8u, N2 - u)});
+                for (uint32_t u = 0; u < N2; ++u) items.push_back({i, u, 0u});
             }
         ck.pf_hi.cnt = (uint32_t)(items.size() - ck.pf_hi.off);
         ck.fin.off = items.size();
@@ -549,11 +549,11 @@ static int run_eval(mmh_handle* h, const double* d_params, double w0, double w1,
         tick(6);
         if (ck.pf_lo.cnt) {
             if (ck.wide) {
-                k_pfin_lo<MAXG><<<(ck.pf_lo.cnt + 7) / 8, 256, 0, st>>>(sp, h->d_items + ck.pf_lo.off, ck.pf_lo.cnt, S);
-                k_pfin_hi<MAXG><<<ck.pf_hi.cnt, 256, 0, st>>>(sp, h->d_items + ck.pf_hi.off, S);
+                k_pfin_lo<MAXG><<<(ck.pf_lo.cnt + 1) / 2, 256, 0, st>>>(sp, h->d_items + ck.pf_lo.off, ck.pf_lo.cnt, S);
+                k_pfin_hi<MAXG><<<(ck.pf_hi.cnt + 1) / 2, 256, 0, st>>>(sp, h->d_items + ck.pf_hi.off, ck.pf_hi.cnt, S);
             } else {
-                k_pfin_lo<MAXT><<<(ck.pf_lo.cnt + 7) / 8, 256, 0, st>>>(sp, h->d_items + ck.pf_lo.off, ck.pf_lo.cnt, S);
-                k_pfin_hi<MAXT><<<ck.pf_hi.cnt, 256, 0, st>>>(sp, h->d_items + ck.pf_hi.off, S);
+                k_pfin_lo<MAXT><<<(ck.pf_lo.cnt + 1) / 2, 256, 0, st>>>(sp, h->d_items + ck.pf_lo.off, ck.pf_lo.cnt, S);
+                k_pfin_hi<MAXT><<<(ck.pf_hi.cnt + 1) / 2, 256, 0, st>>>(sp, h->d_items + ck.pf_hi.off, ck.pf_hi.cnt, S);
             }
             launches += 2;
         }

@@ -868,14 +868,18 @@ k_stats_b(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, u
 // active bit a, the correction c_a(u) = [a in u] g(u) + [a not in u] y(u) x(u + a), g = x y.
 // k_pfin_lo: lane = lo, loop over a slice of hi;  k_pfin_hi: warp = hi, lanes stride over lo.
 // Output layout per space (stP): slices x (NR + KA) x N1 partials, then (NR + KA) x N2.
+// Each warp owns a quarter of the work of its item: table rows [8 rg, 8 rg + 8) and the bits a with a % 4 == rg
+// (few accumulators -> few registers -> enough resident warps to hide the load latency).
+constexpr int PF_RG = 4, PF_ROWS = NR / PF_RG;
 template <int MB>
 __global__ void __launch_bounds__(256)
 k_pfin_lo(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, uint32_t count, double* __restrict__ S)
 {
     const uint32_t wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (wg >= count) return;
-    const Item it = items[wg];                          // a = chunk of 32 lo, b = hi slice
+    if ((wg >> 2) >= count) return;
+    const int rg = wg & 3;
+    const Item it = items[wg >> 2];                     // a = chunk of 32 lo, b = hi slice
     const SpaceDev& sp = spaces[it.space];
     const int KA = sp.KA, K1 = sp.splitA, K2 = KA - K1;
     const uint32_t N1 = 1u << K1, N2 = 1u << K2;
@@ -886,19 +890,21 @@ k_pfin_lo(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, u
     const double* x = S + sp.x_off;
     const double* y = S + sp.y_off;
     const double* T2 = S + sp.tabA + ((uint64_t)NR << K1);
-    double aR[NR], aC[MB];
+    constexpr int NBIT = (MB + PF_RG - 1) / PF_RG;
+    double aR[PF_ROWS], aC[NBIT];
 #pragma unroll
-    for (int r = 0; r < NR; ++r) aR[r] = 0.0;
+    for (int r = 0; r < PF_ROWS; ++r) aR[r] = 0.0;
 #pragma unroll
-    for (int a = 0; a < MB; ++a) aC[a] = 0.0;
+    for (int a = 0; a < NBIT; ++a) aC[a] = 0.0;
     for (uint32_t hi = h0; hi < h1; ++hi) {
         const uint32_t u = (hi << K1) | lo;
         const double xv = valid ? x[u] : 0.0, yv = valid ? y[u] : 0.0;
         const double g = xv * yv;
 #pragma unroll
-        for (int r = 0; r < NR; ++r) aR[r] = fma(T2[((uint64_t)r << K2) + hi], g, aR[r]);
+        for (int r = 0; r < PF_ROWS; ++r) aR[r] = fma(T2[((uint64_t)(rg * PF_ROWS + r) << K2) + hi], g, aR[r]);
 #pragma unroll
-        for (int a = 0; a < MB; ++a) {
+        for (int q = 0; q < NBIT; ++q) {
+            const int a = q * PF_RG + rg;
             if (a < KA) {
                 const uint32_t bit = 1u << a;
                 double xa = 0.0;
@@ -906,37 +912,40 @@ k_pfin_lo(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, u
                 const bool has = (u >> a) & 1u;
                 if (a >= 5 && valid && !has) xa = x[u | bit];
                 const double c = has ? g : yv * xa;
-                aC[a] = fma(T2[((uint64_t)sp.evA[a] << K2) + hi], c, aC[a]);
+                aC[q] = fma(T2[((uint64_t)sp.evA[a] << K2) + hi], c, aC[q]);
             }
         }
     }
     if (!valid) return;
     double* out = S + sp.stP + (uint64_t)it.b * (NR + KA) * N1;
 #pragma unroll
-    for (int r = 0; r < NR; ++r) out[(uint64_t)r * N1 + lo] = aR[r];
+    for (int r = 0; r < PF_ROWS; ++r) out[(uint64_t)(rg * PF_ROWS + r) * N1 + lo] = aR[r];
 #pragma unroll
-    for (int a = 0; a < MB; ++a) if (a < KA) out[(uint64_t)(NR + a) * N1 + lo] = aC[a];
+    for (int q = 0; q < NBIT; ++q) { const int a = q * PF_RG + rg; if (a < KA) out[(uint64_t)(NR + a) * N1 + lo] = aC[q]; }
 }
 
 template <int MB>
 __global__ void __launch_bounds__(256)
-k_pfin_hi(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, double* __restrict__ S)
+k_pfin_hi(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, uint32_t count, double* __restrict__ S)
 {
-    const Item it = items[blockIdx.x];                  // a = first hi, b = count (one warp each)
+    const uint32_t wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if ((wg >> 2) >= count) return;
+    const int rg = wg & 3;
+    const Item it = items[wg >> 2];                     // a = hi
     const SpaceDev& sp = spaces[it.space];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if ((uint32_t)w >= it.b) return;
     const int KA = sp.KA, K1 = sp.splitA, K2 = KA - K1;
     const uint32_t N1 = 1u << K1, N2 = 1u << K2;
-    const uint32_t hi = it.a + w;
+    const uint32_t hi = it.a;
     const double* x = S + sp.x_off;
     const double* y = S + sp.y_off;
     const double* T1 = S + sp.tabA;
-    double aR[NR], aC[MB];
+    constexpr int NBIT = (MB + PF_RG - 1) / PF_RG;
+    double aR[PF_ROWS], aC[NBIT];
 #pragma unroll
-    for (int r = 0; r < NR; ++r) aR[r] = 0.0;
+    for (int r = 0; r < PF_ROWS; ++r) aR[r] = 0.0;
 #pragma unroll
-    for (int a = 0; a < MB; ++a) aC[a] = 0.0;
+    for (int a = 0; a < NBIT; ++a) aC[a] = 0.0;
     for (uint32_t l0 = 0; l0 < N1; l0 += 32) {
         const uint32_t lo = l0 + lane;
         const bool valid = lo < N1;
@@ -944,9 +953,10 @@ k_pfin_hi(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, d
         const double xv = valid ? x[u] : 0.0, yv = valid ? y[u] : 0.0;
         const double g = xv * yv;
 #pragma unroll
-        for (int r = 0; r < NR; ++r) aR[r] = fma(valid ? T1[((uint64_t)r << K1) + lo] : 0.0, g, aR[r]);
+        for (int r = 0; r < PF_ROWS; ++r) aR[r] = fma(valid ? T1[((uint64_t)(rg * PF_ROWS + r) << K1) + lo] : 0.0, g, aR[r]);
 #pragma unroll
-        for (int a = 0; a < MB; ++a) {
+        for (int q = 0; q < NBIT; ++q) {
+            const int a = q * PF_RG + rg;
             if (a < KA) {
                 const uint32_t bit = 1u << a;
                 double xa = 0.0;
@@ -954,16 +964,18 @@ k_pfin_hi(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, d
                 const bool has = (u >> a) & 1u;
                 if (a >= 5 && valid && !has) xa = x[u | bit];
                 const double c = has ? g : yv * xa;
-                aC[a] = fma(valid ? T1[((uint64_t)sp.evA[a] << K1) + lo] : 0.0, c, aC[a]);
+                aC[q] = fma(valid ? T1[((uint64_t)sp.evA[a] << K1) + lo] : 0.0, c, aC[q]);
             }
         }
     }
     double* out = S + sp.stP + (uint64_t)sp.slices * (NR + KA) * N1;
 #pragma unroll
-    for (int r = 0; r < NR; ++r) { const double t = warp_sum(aR[r]); if (lane == 0) out[(uint64_t)r * N2 + hi] = t; }
+    for (int r = 0; r < PF_ROWS; ++r) { const double t = warp_sum(aR[r]); if (lane == 0) out[(uint64_t)(rg * PF_ROWS + r) * N2 + hi] = t; }
 #pragma unroll
-    for (int a = 0; a < MB; ++a)
-        if (a < KA) { const double t = warp_sum(aC[a]); if (lane == 0) out[(uint64_t)(NR + a) * N2 + hi] = t; }
+    for (int q = 0; q < NBIT; ++q) {
+        const int a = q * PF_RG + rg;
+        if (a < KA) { const double t = warp_sum(aC[q]); if (lane == 0) out[(uint64_t)(NR + a) * N2 + hi] = t; }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
