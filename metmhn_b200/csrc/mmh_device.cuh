@@ -515,7 +515,36 @@ __device__ __forceinline__ void rate4(const BitDesc& d, uint32_t p0, double (&r)
     }
 }
 
-template <bool ADJ>
+// MODE 1: pair with two plain tables and KA >= 7 -> bits below KA read four consecutive table entries, bits of
+//         group B one scalar.  MODE 2: product tables (single group): four consecutive entries of the low-part
+//         table times one scalar of the high-part table.  MODE 0: anything else (generic indexing).
+// The modes are separate instantiations selected once per CTA, which keeps the index-class branches of factor4
+// (otherwise if-converted into one long predicated sequence, profiles/r1_v6*) out of the hot loop.
+__device__ __forceinline__ int solve_mode(const SpaceDev& sp)
+{
+    if (sp.kind == K_JOINT) return (!sp.splitA && !sp.splitB && sp.KA >= 7) ? 1 : 0;
+    return sp.splitA ? 2 : 0;
+}
+
+template <int MODE>
+__device__ __forceinline__ void rate4m(const SpaceCtx& c, int a, uint32_t p0, double (&r)[4])
+{
+    const BitDesc& d = c.bit[a];
+    if (MODE == 0) { rate4(d, p0, r); return; }
+    if (MODE == 1 && a >= c.KA) {
+        const double k = d.p1[p0 >> c.KA];
+        r[0] = k; r[1] = k; r[2] = k; r[3] = k;
+        return;
+    }
+    const double2* q = reinterpret_cast<const double2*>(d.p1 + (p0 & d.m1));
+    const double2 u = q[0], w = q[1];
+    if (MODE == 2) {
+        const double k = d.p2[(p0 >> d.sh2) & d.m2];
+        r[0] = u.x * k; r[1] = u.y * k; r[2] = w.x * k; r[3] = w.y * k;
+    } else { r[0] = u.x; r[1] = u.y; r[2] = w.x; r[3] = w.y; }
+}
+
+template <bool ADJ, int MODE>
 __device__ __forceinline__ void solve_block4(const SpaceDev& sp, const SpaceDev* __restrict__ spaces, const SpaceCtx& c,
                                              double* __restrict__ S, uint32_t hi, int lane)
 {
@@ -540,7 +569,7 @@ __device__ __forceinline__ void solve_block4(const SpaceDev& sp, const SpaceDev*
             const uint32_t bit = 1u << a;
             const uint32_t p0 = ADJ ? s0 : (s0 ^ bit);
             const double2* qv = reinterpret_cast<const double2*>(v + (on ? (ADJ ? (s0 | bit) : p0) : s0));
-            rate4(c.bit[a], on ? p0 : s0, rr[q]);
+            rate4m<MODE>(c, a, on ? p0 : s0, rr[q]);
             va[q] = qv[0]; vb[q] = qv[1];
             if (!on) { rr[q][0] = 0.0; rr[q][1] = 0.0; rr[q][2] = 0.0; rr[q][3] = 0.0; va[q] = make_double2(0.0, 0.0); vb[q] = va[q]; }
         }
@@ -553,15 +582,23 @@ __device__ __forceinline__ void solve_block4(const SpaceDev& sp, const SpaceDev*
     // diagonal
     {
         double dA[4], dB[4];
-        factor4(c.dA, 0, c.mA, s0, dA);
-        factor4(c.dB, (uint32_t)c.KA, c.mB, s0, dB);
+        if (MODE == 0) {
+            factor4(c.dA, 0, c.mA, s0, dA);
+            factor4(c.dB, (uint32_t)c.KA, c.mB, s0, dB);
+        } else {
+            const double2* q = reinterpret_cast<const double2*>(c.dA + (s0 & c.mA));
+            const double2 u = q[0], w = q[1];
+            dA[0] = u.x; dA[1] = u.y; dA[2] = w.x; dA[3] = w.y;
+            const double k = MODE == 1 ? c.dB[s0 >> c.KA] : 0.0;
+            dB[0] = k; dB[1] = k; dB[2] = k; dB[3] = k;
+        }
 #pragma unroll
         for (int t = 0; t < 4; ++t) inv[t] = 1.0 / (dA[t] + dB[t]);
     }
     // edges inside the lane: bit 0 from t = 0 and t = 2, bit 1 from t = 0 and t = 1
-    rate4(c.bit[0], s0, r);
+    rate4m<MODE>(c, 0, s0, r);
     const double e0_0 = r[0], e0_2 = r[2];
-    rate4(c.bit[1], s0, r);
+    rate4m<MODE>(c, 1, s0, r);
     const double e1_0 = r[0], e1_1 = r[1];
     // edges across lanes (bits 2..6): rate at the state that lacks the bit
     double rl[5][4];
@@ -569,7 +606,7 @@ __device__ __forceinline__ void solve_block4(const SpaceDev& sp, const SpaceDev*
     for (int a = 0; a < 5; ++a) {
         const uint32_t bit = 4u << a;
         const bool has = (s0 & bit) != 0;
-        if (ADJ ? !has : has) rate4(c.bit[a + 2], ADJ ? s0 : (s0 ^ bit), rl[a]);
+        if (ADJ ? !has : has) rate4m<MODE>(c, a + 2, ADJ ? s0 : (s0 ^ bit), rl[a]);
         else { rl[a][0] = 0.0; rl[a][1] = 0.0; rl[a][2] = 0.0; rl[a][3] = 0.0; }
     }
     const int pl = __popc(lane);
@@ -628,10 +665,21 @@ k_solve_small4(const SpaceDev* __restrict__ spaces, const uint32_t* __restrict__
     ctx_build(ctx[wl], sp, S, lane);
     __syncwarp();
     const uint32_t nblk = 1u << (sp.KA + sp.KB - 7);
+    const int mode = solve_mode(sp);
     if (!ADJ) {
-        for (uint32_t hi = 0; hi < nblk; ++hi) { solve_block4<false>(sp, spaces, ctx[wl], S, hi, lane); __syncwarp(); }
+        for (uint32_t hi = 0; hi < nblk; ++hi) {
+            if (mode == 1) solve_block4<false, 1>(sp, spaces, ctx[wl], S, hi, lane);
+            else if (mode == 2) solve_block4<false, 2>(sp, spaces, ctx[wl], S, hi, lane);
+            else solve_block4<false, 0>(sp, spaces, ctx[wl], S, hi, lane);
+            __syncwarp();
+        }
     } else {
-        for (uint32_t hi = nblk; hi-- > 0;) { solve_block4<true>(sp, spaces, ctx[wl], S, hi, lane); __syncwarp(); }
+        for (uint32_t hi = nblk; hi-- > 0;) {
+            if (mode == 1) solve_block4<true, 1>(sp, spaces, ctx[wl], S, hi, lane);
+            else if (mode == 2) solve_block4<true, 2>(sp, spaces, ctx[wl], S, hi, lane);
+            else solve_block4<true, 0>(sp, spaces, ctx[wl], S, hi, lane);
+            __syncwarp();
+        }
     }
 }
 
@@ -645,8 +693,10 @@ k_solve_big4(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs,
     ctx_build(ctx, sp, S, threadIdx.x);
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (uint32_t r = w; r < sg.b; r += nw)
-        solve_block4<ADJ>(sp, spaces, ctx, S, hs[sg.a + r], lane);
+    const int mode = solve_mode(sp);
+    if (mode == 1)      for (uint32_t r = w; r < sg.b; r += nw) solve_block4<ADJ, 1>(sp, spaces, ctx, S, hs[sg.a + r], lane);
+    else if (mode == 2) for (uint32_t r = w; r < sg.b; r += nw) solve_block4<ADJ, 2>(sp, spaces, ctx, S, hs[sg.a + r], lane);
+    else                for (uint32_t r = w; r < sg.b; r += nw) solve_block4<ADJ, 0>(sp, spaces, ctx, S, hs[sg.a + r], lane);
 }
 
 // per-patient log-likelihood (likelihood.py:316,350,384,405,438)
