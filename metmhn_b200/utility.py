@@ -50,6 +50,45 @@ def cross_val(dat, penal_fun, splits, n_folds: int, m_p_corr: float, seed: int =
     return runs
 
 
+def cross_val_distributed(dat, penal_fun, splits, n_folds: int, m_p_corr: float, seed: int = 42,
+                          rank: int = 0, world: int = 1, device: int = 0, group=None, fit_and_score=None):
+    """The same sweep with the (lambda, fold) jobs dealt round-robin to the ranks of a torch.distributed group (one
+    process per GPU, BASELINE config 5): the 25 fits of the default 5 x 5 sweep are independent, so there is no
+    data-path collective, only one all-reduce of the (n_folds, len(splits)) result table at the end.
+    `fit_and_score(train, test, lam) -> float` defaults to `learn_mhn` + `score` on this rank's GPU."""
+    dat = np.asarray(dat)
+    splits = np.asarray(splits, dtype=float)
+    shuffled = dat[np.random.Generator(np.random.PCG64(seed)).permutation(dat.shape[0])]
+    batch = int(np.ceil(dat.shape[0] / n_folds))
+    if fit_and_score is None:
+        from .regularized_optimization import dataset_handle
+
+        def fit_and_score(train, test, lam):
+            th0, dp0, dm0 = indep(train)
+            htrain = dataset_handle(train, device=device)
+            th, dp, dm = learn_mhn(th0, dp0, dm0, htrain, m_p_corr, penal_fun, lam, opt_v=False)
+            return dataset_handle(test, device=device).value(np.concatenate([th.ravel(), dp, dm]), m_p_corr)
+
+    runs = np.zeros((n_folds, splits.shape[0]))
+    jobs = [(i, f) for i in range(splits.shape[0]) for f in range(n_folds)]
+    for j, (i, fold) in enumerate(jobs):
+        if j % world != rank:
+            continue
+        start, stop = batch * fold, min(batch * (fold + 1), dat.shape[0])
+        train = np.ascontiguousarray(np.concatenate([shuffled[:start], shuffled[stop:]]))
+        test = np.ascontiguousarray(shuffled[start:stop])
+        runs[fold, i] = fit_and_score(train, test, float(splits[i]))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        t = torch.from_numpy(runs)
+        if dist.get_backend(group) == "nccl":
+            t = t.cuda(device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        runs = t.cpu().numpy()
+    return runs
+
+
 def categorize(paired, meta_status):
     """Row type from the annotation columns (`Utilityfunctions.py:98-113`); None = unusable row."""
     if paired == 0:

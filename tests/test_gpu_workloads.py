@@ -76,3 +76,15 @@ def test_learn_mhn_converges_and_matches_oracle_objective():
     assert np.abs(g).max() < 5e-3
     f_ref, g_ref = rr.score_and_grad_reg(x, dat, 0.65, rr.symmetric_penal, lam)
     assert abs(float(f) - f_ref) <= 1e-10 * abs(f_ref) and rel_err(g, g_ref) <= 1e-8
+
+
+def test_cross_val_sweep_runs_on_gpu():
+    """Utilityfunctions.cross_val (:186-231) mirror: 2 folds x 2 penalty weights on a small synthetic dataset."""
+    import metmhn_b200 as mm
+    from metmhn_b200.simulate import syn_v1
+    from metmhn_b200.utility import cross_val, cross_val_distributed
+    d = syn_v1(5, 120, 515, max_joint_bits=9)
+    runs = cross_val(d["dat"], mm.symmetric_penal, np.array([1e-3, 1e-2]), 2, 0.65)
+    assert runs.shape == (2, 2) and np.isfinite(runs).all() and (runs < 0).all()
+    runs2 = cross_val_distributed(d["dat"], mm.symmetric_penal, np.array([1e-3, 1e-2]), 2, 0.65)
+    assert np.abs(runs - runs2).max() <= 1e-9

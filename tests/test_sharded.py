@@ -86,3 +86,40 @@ def test_world_size_2_gloo_matches_single_process():
     for _, s, g, v, _ in res:
         assert abs(s - s0) <= 1e-12 * abs(s0) and abs(v - s0) <= 1e-12 * abs(s0)
         assert np.abs(g - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
+def _cv_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from metmhn_b200.utility import cross_val_distributed
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d = syn_v1(4, 60, 44)
+    fake = lambda train, test, lam: float(train.shape[0] * 1000 + test[:, :-2].sum() + lam)     # deterministic stand-in for a fit
+    runs = cross_val_distributed(d["dat"], None, np.array([0.1, 0.2, 0.3]), 4, 0.65, rank=rank, world=world, fit_and_score=fake)
+    q.put((rank, runs))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_cross_val_jobs_are_distributed_and_gathered():
+    """BASELINE config 5 (fold x lambda sweep over the GPUs of a box): job distribution + result gathering on gloo."""
+    import torch.multiprocessing as mp
+    from metmhn_b200.utility import cross_val_distributed
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_cv_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=180) for _ in range(2)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    d = syn_v1(4, 60, 44)
+    fake = lambda train, test, lam: float(train.shape[0] * 1000 + test[:, :-2].sum() + lam)
+    single = cross_val_distributed(d["dat"], None, np.array([0.1, 0.2, 0.3]), 4, 0.65, fit_and_score=fake)
+    assert single.shape == (4, 3) and (single != 0).all()
+    for _, runs in res:
+        assert np.array_equal(runs, single)
