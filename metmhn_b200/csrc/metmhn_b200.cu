@@ -104,8 +104,11 @@ static uint64_t space_scratch(SpaceDev& s, uint64_t off)
     if (s.kind == K_JOINT) {
         // group-A statistics sum over uB, group-B statistics over uA: slice the summed range so that lopsided pairs
         // (one tumour with many events, the other with few) still expose enough parallel work
-        s.slices = (uint32_t)std::min<uint64_t>(256, std::max<uint64_t>(1, NB / 128));
-        s.slicesB = (uint32_t)std::min<uint64_t>(256, std::max<uint64_t>(1, NA / 2048));
+        // (the partial tables are capped at 2M doubles: more slices only where the table is small)
+        const uint64_t capA = std::max<uint64_t>(8, (2ull << 20) / ((s.KA + 1) * NA));
+        const uint64_t capB = std::max<uint64_t>(8, (2ull << 20) / ((s.KB + 1) * NB));
+        s.slices = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(256, capA), std::max<uint64_t>(1, NB / 128));
+        s.slicesB = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(256, capB), std::max<uint64_t>(1, NA / 2048));
         s.stA = take((s.KA + 1) * NA);
         s.stB = take((s.KB + 1) * NB);
         s.stP = take((uint64_t)s.slices * (s.KA + 1) * NA);
