@@ -14,6 +14,7 @@
 
 using namespace mmh;
 
+static constexpr int RED_SLICES = 32;            // first stage of the gradient-partials reduction
 static constexpr size_t FIN_SMEM = (size_t)(NACC * NR * NR + FIN_WARPS * NR * 33) * sizeof(double);
 
 static thread_local std::string g_err;
@@ -36,7 +37,8 @@ struct ChunkPlan {
     Range pre4, main_small4, sec_small4;         // small-tier spaces with K >= 7 (four states per lane)
     Range setup, setup_wide, pre, main_small, sec_small, logp, joints, st_a, st_ar, st_b, pf_lo, pf_hi, fin;
     bool wide = false;                           // some group has more than MAXT bits
-    std::vector<Range> main_lv, sec_lv;          // big-tier segments per popcount level
+    std::vector<Range> main_lv, sec_lv;          // big-tier segments per popcount level (generic kernel)
+    std::vector<Range> main_lvt, sec_lvt;        // big-tier tiles per level (tiled kernel)
     uint64_t scratch = 0;                        // doubles
 };
 
@@ -55,17 +57,18 @@ struct mmh_handle {
     uint32_t* d_lists = nullptr;
     Item* d_items = nullptr;
     uint32_t* d_hs = nullptr;
+    uint32_t* d_hsidx = nullptr;                 // [bits][level] -> first entry of that popcount level in d_hs
     uint8_t* d_cls = nullptr;
     double* d_cnt = nullptr;
     EvalPar* d_par = nullptr;
     double *d_params = nullptr, *d_scratch = nullptr, *d_logp = nullptr, *d_partial = nullptr;
-    double *d_diracc = nullptr, *d_tdir = nullptr, *d_out = nullptr, *h_out = nullptr;
+    double *d_partial2 = nullptr, *d_diracc = nullptr, *d_tdir = nullptr, *d_out = nullptr, *h_out = nullptr;
     // Chunks are independent, so they are spread round-robin over NS side streams, each with its own scratch
     // buffer and gradient partials: the thin popcount levels and the tails of one chunk overlap with the work
     // of the others.  Chunk -> stream is static and k_final adds the slots in a fixed order: results stay
     // bit-identical from call to call.
-    static constexpr int NS = 8;                 // slots allocated; `ns` of them are used (MMH_STREAMS, default 6)
-    int ns = 6;
+    static constexpr int NS = 32;                // most side streams; `ns` of them are used (MMH_STREAMS, default 12)
+    int ns = 12;
     cudaStream_t stream = nullptr;               // main stream: parameters, k_prep, k_final, copies
     cudaStream_t side[NS] = {};
     cudaEvent_t ev_side[NS] = {}, ev_prep = nullptr;
@@ -341,15 +344,21 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
             if (sp[i].splitB) for (uint32_t u = 0; u < (1u << sp[i].KB); u += 1024) items.push_back({i, 1u, u});
         }
         ck.setup_wide.cnt = (uint32_t)(items.size() - ck.setup_wide.off);
+        // spaces the tiled solve kernel takes (must agree with tiled_space() on the device side)
+        auto tiled = [&](const SpaceDev& s) {
+            if (bits(s) < BIGK || s.kind == K_PRE) return false;
+            if (s.kind == K_JOINT) return !s.splitA && !s.splitB && s.KA >= 4;
+            return s.splitA >= 4;
+        };
         auto levels_of = [&](auto pred, std::vector<Range>& lv) {
             int maxkh = -1;
-            for (uint32_t i = 0; i < ck.nspaces; ++i) if (pred(sp[i]) && bits(sp[i]) >= BIGK) maxkh = std::max(maxkh, bits(sp[i]) - 7);
+            for (uint32_t i = 0; i < ck.nspaces; ++i) if (pred(sp[i]) && bits(sp[i]) >= BIGK && !tiled(sp[i])) maxkh = std::max(maxkh, bits(sp[i]) - 7);
             if (maxkh < 0) return;
             lv.resize(maxkh + 1);
             for (int l = 0; l <= maxkh; ++l) {
                 lv[l].off = items.size();
                 for (uint32_t i = 0; i < ck.nspaces; ++i) {
-                    if (!pred(sp[i]) || bits(sp[i]) < BIGK) continue;
+                    if (!pred(sp[i]) || bits(sp[i]) < BIGK || tiled(sp[i])) continue;
                     const int kh = bits(sp[i]) - 7;          // blocks of 128 states
                     if (l > kh) continue;
                     need_hs(kh);
@@ -360,8 +369,49 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
                 lv[l].cnt = (uint32_t)(items.size() - lv[l].off);
             }
         };
+        // tiled kernel: rows x column blocks, one launch per level lA + lB; a CTA item is up to TILES_PER_CTA warp
+        // tiles (8 rows x 16 columns) of one (lA, lB) split
+        auto levels_of_t = [&](auto pred, std::vector<Range>& lv) {
+            int maxl = -1;
+            auto dims = [&](const SpaceDev& s, int& kbA, int& kbB) {
+                if (s.kind == K_JOINT) { kbA = s.KA - 4; kbB = s.KB; }
+                else { kbA = s.splitA - 4; kbB = s.KA - s.splitA; }
+            };
+            for (uint32_t i = 0; i < ck.nspaces; ++i)
+                if (pred(sp[i]) && tiled(sp[i])) { int a, b; dims(sp[i], a, b); maxl = std::max(maxl, a + b); }
+            if (maxl < 0) return;
+            lv.resize(maxl + 1);
+            for (int l = 0; l <= maxl; ++l) {
+                lv[l].off = items.size();
+                // thin levels: one tile per warp (the launch is a single wave and its duration the latency of the
+                // tiles a warp runs back to back); fat levels: up to TILES_PER_CTA tiles per CTA
+                uint64_t total = 0;
+                for (int pass = 0; pass < 2; ++pass) {
+                    const uint64_t per_cta = total <= 8ull * 3 * 148 ? 8 : total <= 16ull * 3 * 148 ? 16 : TILES_PER_CTA;
+                    for (uint32_t i = 0; i < ck.nspaces; ++i) {
+                        if (!pred(sp[i]) || !tiled(sp[i])) continue;
+                        int kbA, kbB;
+                        dims(sp[i], kbA, kbB);
+                        if (l > kbA + kbB) continue;
+                        need_hs(kbA); need_hs(kbB);
+                        for (int lA = std::max(0, l - kbB); lA <= std::min(kbA, l); ++lA) {
+                            const int lB = l - lA;
+                            const uint64_t nA = hs_lvl[kbA][lA + 1] - hs_lvl[kbA][lA];
+                            const uint64_t nB = hs_lvl[kbB][lB + 1] - hs_lvl[kbB][lB];
+                            const uint64_t T = nA * ((nB + 7) / 8);
+                            if (pass == 0) { total += T; continue; }
+                            for (uint64_t t0 = 0; t0 < T; t0 += per_cta)
+                                items.push_back({i, (uint32_t)lA | ((uint32_t)lB << 8) | ((uint32_t)std::min<uint64_t>(per_cta, T - t0) << 16), (uint32_t)t0});
+                        }
+                    }
+                }
+                lv[l].cnt = (uint32_t)(items.size() - lv[l].off);
+            }
+        };
         levels_of(is_main, ck.main_lv);
         levels_of(is_sec, ck.sec_lv);
+        levels_of_t(is_main, ck.main_lvt);
+        levels_of_t(is_sec, ck.sec_lvt);
         ck.st_a.off = items.size();
         for (uint32_t i = 0; i < ck.nspaces; ++i)
             if (sp[i].kind == K_JOINT) {
@@ -431,6 +481,12 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
     CK(up((void**)&h->d_lists, lists.data(), lists.size() * sizeof(uint32_t)));
     CK(up((void**)&h->d_items, items.data(), items.size() * sizeof(Item)));
     CK(up((void**)&h->d_hs, hs_all.data(), hs_all.size() * sizeof(uint32_t)));
+    {
+        std::vector<uint32_t> hsidx((size_t)MMH_MAX_BITS * 32, 0u);
+        for (int kb = 0; kb < MMH_MAX_BITS; ++kb)
+            for (size_t l = 0; l < hs_lvl[kb].size() && l < 32; ++l) hsidx[(size_t)kb * 32 + l] = (uint32_t)(hs_off[kb] + hs_lvl[kb][l]);
+        CK(up((void**)&h->d_hsidx, hsidx.data(), hsidx.size() * sizeof(uint32_t)));
+    }
     CK(up((void**)&h->d_cls, cls.data(), cls.size()));
     CK(up((void**)&h->d_cnt, cnt_dm2.data(), NR * sizeof(double)));
     const size_t npar = (size_t)h->n_tot * (h->n_tot + 2);
@@ -448,9 +504,10 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
     h->d_scratch = h->d_scratch_s[0];
     CK(cudaMalloc((void**)&h->d_logp, std::max<int64_t>(n_dat, 1) * sizeof(double)));
     CK(cudaMemset(h->d_logp, 0, std::max<int64_t>(n_dat, 1) * sizeof(double)));
-    CK(cudaMalloc((void**)&h->d_partial, (size_t)mmh_handle::NS * h->fin_ctas * NACC * NR * NR * sizeof(double)));
-    CK(cudaMalloc((void**)&h->d_diracc, (size_t)mmh_handle::NS * 2 * NR * sizeof(double)));
-    CK(cudaMalloc((void**)&h->d_tdir, (size_t)mmh_handle::NS * std::max<uint32_t>(h->max_joints, 1) * 2 * sizeof(double)));
+    CK(cudaMalloc((void**)&h->d_partial, (size_t)h->ns * h->fin_ctas * NACC * NR * NR * sizeof(double)));
+    CK(cudaMalloc((void**)&h->d_partial2, (size_t)RED_SLICES * NACC * NR * NR * sizeof(double)));
+    CK(cudaMalloc((void**)&h->d_diracc, (size_t)h->ns * 2 * NR * sizeof(double)));
+    CK(cudaMalloc((void**)&h->d_tdir, (size_t)h->ns * std::max<uint32_t>(h->max_joints, 1) * 2 * sizeof(double)));
     CK(cudaMalloc((void**)&h->d_out, (npar + 1) * sizeof(double)));
     CK(cudaMallocHost((void**)&h->h_out, (npar + 1) * sizeof(double)));
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -467,7 +524,7 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
 static int enqueue_eval(mmh_handle* h, const double* d_params, double w0, double w1, int want_grad, int64_t* n_launches)
 {
     cudaStream_t st = h->stream;
-    constexpr int NS = mmh_handle::NS;
+    const int NS = h->ns;                               // slots in use (profile mode runs everything in slot 0)
     const int ns = h->profile ? 1 : h->ns;              // profile mode serialises everything on the main stream
     int64_t launches = 0;
     // optional per-class timing (profile mode): CUDA events around every launch group
@@ -526,21 +583,31 @@ static int enqueue_eval(mmh_handle* h, const double* d_params, double w0, double
                 ++launches;
             }
         };
+        auto bigt = [&](const std::vector<Range>& lv, bool adj) {
+            const int L = (int)lv.size();
+            for (int q = 0; q < L; ++q) {
+                const Range& r = lv[adj ? L - 1 - q : q];
+                if (!r.cnt) continue;
+                if (adj) k_solve_tile<true><<<r.cnt, 256, 0, st>>>(sp, h->d_items + r.off, h->d_hs, h->d_hsidx, S);
+                else     k_solve_tile<false><<<r.cnt, 256, 0, st>>>(sp, h->d_items + r.off, h->d_hs, h->d_hsidx, S);
+                ++launches;
+            }
+        };
         tick(0);
         k_setup<<<ck.setup.cnt, 256, 0, st>>>(sp, h->d_items + ck.setup.off, h->d_par, S); ++launches;
         if (ck.setup_wide.cnt) { k_setup_wide<<<ck.setup_wide.cnt, 1024, 0, st>>>(sp, h->d_items + ck.setup_wide.off, h->d_par, S); ++launches; }
         tick(1);
         small(ck.pre, false); small4(ck.pre4, false);
         small(ck.main_small, false); small4(ck.main_small4, false);
-        big(ck.main_lv, false);
+        big(ck.main_lv, false); bigt(ck.main_lvt, false);
         small(ck.sec_small, false); small4(ck.sec_small4, false);
-        big(ck.sec_lv, false);
+        big(ck.sec_lv, false); bigt(ck.sec_lvt, false);
         tick(5);
         if (ck.logp.cnt) { k_logp<<<(ck.logp.cnt + 127) / 128, 128, 0, st>>>(sp, h->d_lists + ck.logp.off, ck.logp.cnt, S, h->d_logp); ++launches; }
         if (!want_grad) continue;
         tick(2);
         small(ck.sec_small, true); small4(ck.sec_small4, true);
-        big(ck.sec_lv, true);
+        big(ck.sec_lv, true); bigt(ck.sec_lvt, true);
         tick(5);
         if (ck.joints.cnt) {
             k_direct<<<(ck.joints.cnt + 255) / 256, 256, 0, st>>>(sp, h->d_lists + ck.joints.off, ck.joints.cnt, S, d_tdir);
@@ -549,7 +616,7 @@ static int enqueue_eval(mmh_handle* h, const double* d_params, double w0, double
         }
         tick(2);
         small(ck.main_small, true); small4(ck.main_small4, true);
-        big(ck.main_lv, true);
+        big(ck.main_lv, true); bigt(ck.main_lvt, true);
         small(ck.pre, true); small4(ck.pre4, true);
         tick(3);
         if (ck.st_a.cnt) {
@@ -583,7 +650,11 @@ static int enqueue_eval(mmh_handle* h, const double* d_params, double w0, double
             CK(cudaStreamWaitEvent(main_stream, h->ev_side[q], 0));
         }
     tick(5);
-    k_final<<<1, 1024, 0, st>>>(h->d_partial, NS * h->fin_ctas, h->d_diracc, NS, h->d_logp, h->d_cls, h->n_dat, h->d_cnt, w0, w1,
+    if (want_grad) {
+        k_reduce_partials<<<dim3(NACC * NR * NR / 256, RED_SLICES), 256, 0, st>>>(h->d_partial, NS * h->fin_ctas, h->d_partial2);
+        ++launches;
+    }
+    k_final<<<1, 1024, 0, st>>>(h->d_partial2, RED_SLICES, h->d_diracc, NS, h->d_logp, h->d_cls, h->n_dat, h->d_cnt, w0, w1,
                                 h->n_tot, want_grad, h->d_out);
     ++launches;
     tick(-1);
@@ -740,7 +811,7 @@ extern "C" void mmh_destroy(mmh_handle* h)
 {
     if (!h) return;
     cudaSetDevice(h->device);
-    cudaFree(h->d_spaces); cudaFree(h->d_lists); cudaFree(h->d_items); cudaFree(h->d_hs); cudaFree(h->d_cls);
+    cudaFree(h->d_spaces); cudaFree(h->d_lists); cudaFree(h->d_items); cudaFree(h->d_hs); cudaFree(h->d_hsidx); cudaFree(h->d_cls);
     cudaFree(h->d_cnt); cudaFree(h->d_par); cudaFree(h->d_params); cudaFree(h->d_logp);
     for (int q = 0; q < mmh_handle::NS; ++q) {
         cudaFree(h->d_scratch_s[q]);
@@ -748,7 +819,7 @@ extern "C" void mmh_destroy(mmh_handle* h)
         if (h->ev_side[q]) cudaEventDestroy(h->ev_side[q]);
     }
     if (h->ev_prep) cudaEventDestroy(h->ev_prep);
-    cudaFree(h->d_partial); cudaFree(h->d_diracc); cudaFree(h->d_tdir); cudaFree(h->d_out);
+    cudaFree(h->d_partial); cudaFree(h->d_partial2); cudaFree(h->d_diracc); cudaFree(h->d_tdir); cudaFree(h->d_out);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->ev0) cudaEventDestroy(h->ev0);

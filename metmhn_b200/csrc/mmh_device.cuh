@@ -23,7 +23,7 @@ constexpr int MAXT    = 16;   // bits per group with one explicit table; wider g
 constexpr int MAXG    = 26;   // bits per group
 constexpr int BIGK    = 13;   // spaces with K >= BIGK are solved by per-level launches
 constexpr int SEGB    = 32;   // blocks of 32 states per big-tier segment (one CTA)
-constexpr int FIN_U   = 256;  // sub-states per finish work item
+constexpr int FIN_U   = 64;   // sub-states per finish work item
 
 enum Kind : uint8_t { K_PRE = 0, K_JOINT = 1, K_PF = 2, K_MF = 3, K_S1 = 4, K_S2 = 5 };
 
@@ -699,6 +699,280 @@ k_solve_big4(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs,
     else                for (uint32_t r = w; r < sg.b; r += nw) solve_block4<ADJ, 0>(sp, spaces, ctx, S, hs[sg.a + r], lane);
 }
 
+// ------------------------------------------------------------------------------------------
+// Tiled solve (big tier, K >= BIGK).  The lattice is viewed as rows x columns:
+//   pair            : columns = group A (KC = KA bits), rows = group B (KR = KB bits); an A-edge's rate is a column
+//                     vector T_A[ev][uA], a B-edge's rate one scalar T_B[ev][uB] per row
+//   product single  : columns = the K1 low bits, rows = the K2 high bits; every rate is a column factor T1[ev][lo]
+//                     times a row factor T2[ev][hi]
+// A warp solves 8 independent rows x 16 consecutive columns: lane = (row group, 4 columns); column bits 0,1 live in
+// the lane's registers, bits 2,3 in the four lanes of a row group (three sub-levels, 3 shuffles per state), all
+// higher bits read 128-byte lines of blocks finished by earlier launches.  The 8 rows of a tile have the same
+// popcount lB and share the column block cA (popcount lA), so every loop of the warp has a uniform trip count and
+// the column-rate loads of the 8 row groups hit the same line.  One launch per level lA + lB.
+constexpr int TILES_PER_CTA = 32;
+
+struct TileCtx {
+    const double* colA[MAXG];          // column bit q: column factor of its rate (T_A[ev] or T1[ev])
+    const double* rowA[MAXG];          // product only: row factor T2[ev] of column bit q
+    const double* rowB[MAXG];          // row bit b: row factor (T_B[ev] or T2[ev])
+    const double* colB[MAXG];          // product only: column factor T1[ev] of row bit b
+    const double* dA;                  // pair: A part of the diagonal; product: the full diagonal vector
+    const double* dB;                  // pair: B part of the diagonal
+    int KC, KR;
+};
+
+__device__ __forceinline__ bool tiled_space(const SpaceDev& sp)
+{
+    if ((int)sp.KA + (int)sp.KB < BIGK || sp.kind == K_PRE) return false;
+    if (sp.kind == K_JOINT) return !sp.splitA && !sp.splitB && sp.KA >= 4;
+    return sp.splitA >= 4;
+}
+
+__device__ __forceinline__ void tile_ctx_build(TileCtx& c, const SpaceDev& sp, const double* __restrict__ S, int t)
+{
+    if (sp.kind == K_JOINT) {
+        const int KA = sp.KA, KB = sp.KB;
+        if (t < KA) { c.colA[t] = S + sp.tabA + ((uint64_t)sp.evA[t] << KA); c.rowA[t] = &c_one; }
+        if (t < KB) { c.rowB[t] = S + sp.tabB + ((uint64_t)sp.evB[t] << KB); c.colB[t] = &c_one; }
+        if (t == 0) {
+            c.dA = S + sp.tabA + ((uint64_t)ROW_D << KA);
+            c.dB = S + sp.tabB + ((uint64_t)ROW_D << KB);
+            c.KC = KA; c.KR = KB;
+        }
+    } else {
+        const int K1 = sp.splitA, K2 = sp.KA - K1;
+        const double* T1 = S + sp.tabA;
+        const double* T2 = T1 + ((uint64_t)NR << K1);
+        if (t < K1) { c.colA[t] = T1 + ((uint64_t)sp.evA[t] << K1); c.rowA[t] = T2 + ((uint64_t)sp.evA[t] << K2); }
+        if (t < K2) { c.rowB[t] = T2 + ((uint64_t)sp.evA[K1 + t] << K2); c.colB[t] = T1 + ((uint64_t)sp.evA[K1 + t] << K1); }
+        if (t == 0) { c.dA = T2 + ((uint64_t)NR << K2); c.dB = &c_zero; c.KC = K1; c.KR = K2; }
+    }
+}
+
+__device__ __forceinline__ void ld4(const double* __restrict__ p, double (&f)[4])
+{
+    const double2* q = reinterpret_cast<const double2*>(p);
+    const double2 a = q[0], b = q[1];
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+}
+
+template <bool ADJ, bool PROD>
+__device__ __forceinline__ void solve_tile16(const SpaceDev& sp, const SpaceDev* __restrict__ spaces, const TileCtx& c,
+                                             double* __restrict__ S, uint32_t cA, uint32_t row, bool valid, int lane)
+{
+    const int KC = c.KC, KR = c.KR;
+    const int lc = lane & 3;
+    const uint32_t lo0 = (cA << 4) | ((uint32_t)lc << 2);
+    const uint32_t s0 = (row << KC) | lo0;
+    double* v = S + (ADJ ? sp.x_off : sp.y_off);
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    // ---- right-hand side: non-zero on few states only (except the second phase's start vector) ----
+    {
+        const uint32_t NC = 1u << KC, NRW = 1u << KR;
+        bool any;
+        if (!ADJ) {
+            if (sp.kind == K_JOINT) any = row < (1u << sp.nb) && ((row ^ lo0) & ~3u) == 0u;
+            else if (sp.kind == K_PF || sp.kind == K_MF) any = true;
+            else any = s0 == 0u;
+        } else {
+            if (sp.kind == K_JOINT) any = (sp.has_pf && (lo0 | 3u) == NC - 1u) || (sp.has_mf && row == NRW - 1u);
+            else any = (s0 | 3u) == (NC << KR) - 1u;
+        }
+        if (any) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) acc[t] = ADJ ? rhs_adj(sp, spaces, S, s0 + t) : rhs_fwd(sp, spaces, S, s0 + t);
+        }
+    }
+    // Edges are taken NB at a time, all loads of a round before its FMAs: a tile is a chain of dependent rounds and
+    // thin levels have no other warps to hide the memory latency behind.
+    // ---- column bits >= 4 (uniform over the warp): FWD visits the set bits of cA, ADJ the unset ones ----
+    {
+        constexpr int NB = 2;
+        uint32_t m = ADJ ? (~cA & ((1u << (KC - 4)) - 1u)) : cA;
+        while (m) {
+            double r[NB][4], y[NB][4], k[NB];
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+                const bool on = m != 0u;
+                const int a = on ? __ffs(m) + 3 : 4;
+                m &= m - 1;
+                const uint32_t bit = 1u << a;
+                k[q] = 1.0;
+                if (on) {
+                    ld4(c.colA[a] + (ADJ ? lo0 : (lo0 ^ bit)), r[q]);
+                    ld4(v + (s0 ^ bit), y[q]);
+                    if (PROD) k[q] = c.rowA[a][row];
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) { r[q][t] = 0.0; y[q][t] = 0.0; }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < NB; ++q)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) acc[t] = fma(PROD ? r[q][t] * k[q] : r[q][t], y[q][t], acc[t]);
+        }
+    }
+    // ---- row bits (same count in every row group of the warp) ----
+    {
+        constexpr int NB = 3;
+        uint32_t m = ADJ ? (~row & ((1u << KR) - 1u)) : row;
+        while (m) {
+            double y[NB][4], k[NB];
+            int bq[NB];
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+                const bool on = m != 0u;
+                const int b = on ? __ffs(m) - 1 : 0;
+                m &= m - 1;
+                bq[q] = b;
+                const uint32_t orow = row ^ (1u << b);
+                if (on) {
+                    k[q] = c.rowB[b][ADJ ? row : orow];
+                    ld4(v + (((uint64_t)orow << KC) | lo0), y[q]);
+                } else {
+                    k[q] = 0.0;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) y[q][t] = 0.0;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+                if (PROD) {
+                    double cf[4];
+                    ld4(c.colB[bq[q]] + lo0, cf);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) acc[t] = fma(cf[t] * k[q], y[q][t], acc[t]);
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) acc[t] = fma(k[q], y[q][t], acc[t]);
+                }
+            }
+        }
+    }
+    // ---- diagonal ----
+    double inv[4];
+    {
+        double d[4];
+        if (PROD) ld4(c.dA + s0, d);
+        else {
+            ld4(c.dA + lo0, d);
+            const double k = c.dB[row];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) d[t] += k;
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) inv[t] = 1.0 / d[t];
+    }
+    // ---- column bits 0,1 (inside the lane) and 2,3 (across the four lanes of the row group) ----
+    double k0 = 1.0, k1 = 1.0, k2 = 1.0, k3 = 1.0;
+    if (PROD) { k0 = c.rowA[0][row]; k1 = c.rowA[1][row]; k2 = c.rowA[2][row]; k3 = c.rowA[3][row]; }
+    double e0a, e0b, e1a, e1b;
+    {
+        const double2* q0 = reinterpret_cast<const double2*>(c.colA[0] + lo0);
+        const double2* q1 = reinterpret_cast<const double2*>(c.colA[1] + lo0);
+        const double2 u = q1[0];
+        e0a = q0[0].x * k0; e0b = q0[1].x * k0;      // bit 0: 0 -> 1, 2 -> 3
+        e1a = u.x * k1; e1b = u.y * k1;              // bit 1: 0 -> 2, 1 -> 3
+    }
+    double w0[4] = {0.0, 0.0, 0.0, 0.0}, w1a[4] = {0.0, 0.0, 0.0, 0.0}, w1b[4] = {0.0, 0.0, 0.0, 0.0};
+    const int pl = __popc(lc);
+    if (!ADJ) {
+        // round 0: lanes 1, 2 receive from lane 0;  round 1: lane 3 receives from lanes 2 (bit 2) and 1 (bit 3)
+        if (pl == 1) {
+            const int q = lc == 2;
+            ld4(c.colA[2 + q] + (lo0 ^ (4u << q)), w0);
+            const double k = q ? k3 : k2;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) w0[t] *= k;
+        } else if (lc == 3) {
+            ld4(c.colA[2] + (lo0 ^ 4u), w1a);
+            ld4(c.colA[3] + (lo0 ^ 8u), w1b);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { w1a[t] *= k2; w1b[t] *= k3; }
+        }
+    } else {
+        // round 0: lanes 1, 2 receive from lane 3;  round 1: lane 0 receives from lanes 1 (bit 2) and 2 (bit 3)
+        if (pl == 1) {
+            const int q = lc == 1;                   // the bit this lane lacks
+            ld4(c.colA[2 + q] + lo0, w0);
+            const double k = q ? k3 : k2;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) w0[t] *= k;
+        } else if (lc == 0) {
+            ld4(c.colA[2] + lo0, w1a);
+            ld4(c.colA[3] + lo0, w1b);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { w1a[t] *= k2; w1b[t] *= k3; }
+        }
+    }
+    double val[4];
+    auto fin = [&]() {
+        if (!ADJ) {
+            val[0] = acc[0] * inv[0];
+            val[1] = fma(e0a, val[0], acc[1]) * inv[1];
+            val[2] = fma(e1a, val[0], acc[2]) * inv[2];
+            val[3] = fma(e0b, val[2], fma(e1b, val[1], acc[3])) * inv[3];
+        } else {
+            val[3] = acc[3] * inv[3];
+            val[2] = fma(e0b, val[3], acc[2]) * inv[2];
+            val[1] = fma(e1b, val[3], acc[1]) * inv[1];
+            val[0] = fma(e0a, val[1], fma(e1a, val[2], acc[0])) * inv[0];
+        }
+    };
+    // Values of lanes that are not final yet are finite partial results and only ever meet a zero weight.
+    fin();
+    {
+        const int src = ADJ ? (lane | 3) : (lane & ~3);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) acc[t] = fma(w0[t], __shfl_sync(0xffffffffu, val[t], src), acc[t]);
+    }
+    fin();
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const double p = __shfl_xor_sync(0xffffffffu, val[t], 1);
+        const double q = __shfl_xor_sync(0xffffffffu, val[t], 2);
+        acc[t] = fma(w1b[t], q, fma(w1a[t], p, acc[t]));
+    }
+    fin();
+    if (valid) {
+        double2* o = reinterpret_cast<double2*>(v + s0);
+        o[0] = make_double2(val[0], val[1]);
+        o[1] = make_double2(val[2], val[3]);
+    }
+}
+
+// item: space, a = lA | lB << 8 | tiles << 16, b = first tile; tile t -> column block t / nBg, row group t % nBg
+template <bool ADJ>
+__global__ void __launch_bounds__(256, 3)
+k_solve_tile(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs, const uint32_t* __restrict__ hs,
+             const uint32_t* __restrict__ hsidx, double* __restrict__ S)
+{
+    __shared__ TileCtx ctx;
+    const Item sg = segs[blockIdx.x];
+    const SpaceDev& sp = spaces[sg.space];
+    tile_ctx_build(ctx, sp, S, threadIdx.x);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t lA = sg.a & 255u, lB = (sg.a >> 8) & 255u, cnt = sg.a >> 16;
+    const uint32_t offA = hsidx[(ctx.KC - 4) * 32 + lA];
+    const uint32_t offB = hsidx[ctx.KR * 32 + lB];
+    const uint32_t nB = hsidx[ctx.KR * 32 + lB + 1] - offB;
+    const uint32_t nBg = (nB + 7u) >> 3;
+    const bool prod = sp.kind != K_JOINT;
+    for (uint32_t q = w; q < cnt; q += 8) {
+        const uint32_t t = sg.b + q;
+        const uint32_t iA = t / nBg, jB = t - iA * nBg;
+        const uint32_t ri = jB * 8u + (uint32_t)(lane >> 2);
+        const bool valid = ri < nB;
+        const uint32_t cA = hs[offA + iA];
+        const uint32_t row = hs[offB + min(ri, nB - 1u)];
+        if (prod) solve_tile16<ADJ, true>(sp, spaces, ctx, S, cA, row, valid, lane);
+        else      solve_tile16<ADJ, false>(sp, spaces, ctx, S, cA, row, valid, lane);
+    }
+}
+
 // per-patient log-likelihood (likelihood.py:316,350,384,405,438)
 __global__ void k_logp(const SpaceDev* __restrict__ spaces, const uint32_t* __restrict__ list, uint32_t count,
                        const double* __restrict__ S, double* __restrict__ logp)
@@ -1170,6 +1444,17 @@ k_finish(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, ui
     }
     double* out = partial + (size_t)blockIdx.x * NACC * NR * NR;
     for (int t = threadIdx.x; t < NACC * NR * NR; t += blockDim.x) out[t] += G[t];     // same CTA index, chunk after chunk
+}
+
+// first stage of the partials reduction: slice y of the CTA range, fixed order inside a slice
+__global__ void k_reduce_partials(const double* __restrict__ partial, int n_cta, double* __restrict__ out)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int per = (n_cta + gridDim.y - 1) / gridDim.y;
+    const int c0 = blockIdx.y * per, c1 = min(n_cta, c0 + per);
+    double s = 0.0;
+    for (int c = c0; c < c1; ++c) s += partial[(size_t)c * NACC * NR * NR + e];
+    out[(size_t)blockIdx.y * NACC * NR * NR + e] = s;
 }
 
 // ------------------------------------------------------------------------------------------
