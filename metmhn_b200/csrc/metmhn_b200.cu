@@ -35,7 +35,7 @@ struct ChunkPlan {
     uint64_t space0 = 0;
     uint32_t nspaces = 0;
     Range pre4, main_small4, sec_small4;         // small-tier spaces with K >= 7 (four states per lane)
-    Range setup, setup_wide, pre, main_small, sec_small, logp, joints, st_a, st_ar, st_b, pf_lo, pf_hi, fin;
+    Range setup, setup_wide, diag, pre, main_small, sec_small, logp, joints, st_a, st_ar, st_b, pf_lo, pf_hi, fin;
     bool wide = false;                           // some group has more than MAXT bits
     std::vector<Range> main_lv, sec_lv;          // big-tier segments per popcount level (generic kernel)
     std::vector<Range> main_lvt, sec_lvt;        // big-tier tiles per level (tiled kernel)
@@ -338,12 +338,23 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
             if (sp[i].kind == K_JOINT) setup_items(i, 1, sp[i].KB, sp[i].splitB);
         }
         ck.setup.cnt = (uint32_t)(items.size() - ck.setup.off);
+        auto is_prod = [](const SpaceDev& s) { return s.kind != K_JOINT && s.kind != K_PRE && s.splitA; };
         ck.setup_wide.off = items.size();
         for (uint32_t i = 0; i < ck.nspaces; ++i) {
+            if (is_prod(sp[i])) continue;
             if (sp[i].splitA) for (uint32_t u = 0; u < (1u << sp[i].KA); u += 1024) items.push_back({i, 0u, u});
             if (sp[i].splitB) for (uint32_t u = 0; u < (1u << sp[i].KB); u += 1024) items.push_back({i, 1u, u});
         }
         ck.setup_wide.cnt = (uint32_t)(items.size() - ck.setup_wide.off);
+        ck.diag.off = items.size();
+        for (uint32_t i = 0; i < ck.nspaces; ++i)
+            if (is_prod(sp[i])) {
+                const uint32_t nlo = std::max<uint32_t>(1u, (1u << sp[i].splitA) >> 7);
+                const uint32_t nhi = std::max<uint32_t>(1u, (1u << (sp[i].KA - sp[i].splitA)) >> 4);
+                for (uint32_t hb = 0; hb < nhi; ++hb)
+                    for (uint32_t lb = 0; lb < nlo; ++lb) items.push_back({i, lb, hb});
+            }
+        ck.diag.cnt = (uint32_t)(items.size() - ck.diag.off);
         // spaces the tiled solve kernel takes (must agree with tiled_space() on the device side)
         auto tiled = [&](const SpaceDev& s) {
             if (bits(s) < BIGK || s.kind == K_PRE) return false;
@@ -435,11 +446,10 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
                 for (uint32_t sl = 0; sl < sp[i].slicesB; ++sl)
                     for (uint32_t u = 0; u < (1u << sp[i].KB); ++u) items.push_back({i, u, sl});
         ck.st_b.cnt = (uint32_t)(items.size() - ck.st_b.off);
-        auto is_prod = [](const SpaceDev& s) { return s.kind != K_JOINT && s.kind != K_PRE && s.splitA; };
         ck.pf_lo.off = items.size();
         for (uint32_t i = 0; i < ck.nspaces; ++i)
             if (is_prod(sp[i])) {
-                const uint32_t nch = std::max<uint32_t>(1u, (1u << sp[i].splitA) >> 5);
+                const uint32_t nch = std::max<uint32_t>(1u, (1u << sp[i].splitA) >> 7);     // blocks of 128 lo
                 for (uint32_t sl = 0; sl < sp[i].slices; ++sl)
                     for (uint32_t c = 0; c < nch; ++c) items.push_back({i, c, sl});
             }
@@ -448,7 +458,7 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
         for (uint32_t i = 0; i < ck.nspaces; ++i)
             if (is_prod(sp[i])) {
                 const uint32_t N2 = 1u << (sp[i].KA - sp[i].splitA);
-                for (uint32_t u = 0; u < N2; ++u) items.push_back({i, u, 0u});
+                for (uint32_t u = 0; u < N2; u += PF_HB) items.push_back({i, u / PF_HB, 0u});
             }
         ck.pf_hi.cnt = (uint32_t)(items.size() - ck.pf_hi.off);
         ck.fin.off = items.size();
@@ -596,6 +606,7 @@ static int enqueue_eval(mmh_handle* h, const double* d_params, double w0, double
         tick(0);
         k_setup<<<ck.setup.cnt, 256, 0, st>>>(sp, h->d_items + ck.setup.off, h->d_par, S); ++launches;
         if (ck.setup_wide.cnt) { k_setup_wide<<<ck.setup_wide.cnt, 1024, 0, st>>>(sp, h->d_items + ck.setup_wide.off, h->d_par, S); ++launches; }
+        if (ck.diag.cnt) { k_diag_prod<<<ck.diag.cnt, 256, 0, st>>>(sp, h->d_items + ck.diag.off, S); ++launches; }
         tick(1);
         small(ck.pre, false); small4(ck.pre4, false);
         small(ck.main_small, false); small4(ck.main_small4, false);
@@ -627,13 +638,8 @@ static int enqueue_eval(mmh_handle* h, const double* d_params, double w0, double
         }
         tick(6);
         if (ck.pf_lo.cnt) {
-            if (ck.wide) {
-                k_pfin_lo<MAXG><<<(ck.pf_lo.cnt + 1) / 2, 256, 0, st>>>(sp, h->d_items + ck.pf_lo.off, ck.pf_lo.cnt, S);
-                k_pfin_hi<MAXG><<<(ck.pf_hi.cnt + 1) / 2, 256, 0, st>>>(sp, h->d_items + ck.pf_hi.off, ck.pf_hi.cnt, S);
-            } else {
-                k_pfin_lo<MAXT><<<(ck.pf_lo.cnt + 1) / 2, 256, 0, st>>>(sp, h->d_items + ck.pf_lo.off, ck.pf_lo.cnt, S);
-                k_pfin_hi<MAXT><<<(ck.pf_hi.cnt + 1) / 2, 256, 0, st>>>(sp, h->d_items + ck.pf_hi.off, ck.pf_hi.cnt, S);
-            }
+            k_pf_lo<<<ck.pf_lo.cnt, 128, 0, st>>>(sp, h->d_items + ck.pf_lo.off, S);
+            k_pf_hi<<<ck.pf_hi.cnt, 128, 0, st>>>(sp, h->d_items + ck.pf_hi.off, S);
             launches += 2;
         }
         tick(4);

@@ -1184,124 +1184,243 @@ k_stats_b(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, u
 }
 
 // ------------------------------------------------------------------------------------------
-// Single-tumour spaces in product form (K1 low bits, K2 high bits; rate(r,u) = T1[r][lo] T2[r][hi]).
-// Their gradient needs, per table row r, the weighted marginals
-//     H1[r][lo] = sum_hi T2[r][hi] E_r(hi,lo)        H2[r][hi] = sum_lo T1[r][lo] E_r(hi,lo)
-// (a 32 x 2^K2 by 2^K2 x 2^K1 product and its mirror image: this is where the reference spends its
-// n_tot-fold x_partial_Q_y passes, vanilla.py:328-393).  E_r = -g for every row, plus, for the row of an
-// active bit a, the correction c_a(u) = [a in u] g(u) + [a not in u] y(u) x(u + a), g = x y.
-// k_pfin_lo: lane = lo, loop over a slice of hi;  k_pfin_hi: warp = hi, lanes stride over lo.
-// Output layout per space (stP): slices x (NR + KA) x N1 partials, then (NR + KA) x N2.
-// Each warp owns a quarter of the work of its item: table rows [8 rg, 8 rg + 8) and the bits a with a % 4 == rg
-// (few accumulators -> few registers -> enough resident warps to hide the load latency).
-constexpr int PF_RG = 4, PF_ROWS = NR / PF_RG;
-template <int MB>
-__global__ void __launch_bounds__(256)
-k_pfin_lo(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, uint32_t count, double* __restrict__ S)
+// Single-tumour spaces in product form (K1 low bits "lo", K2 high bits "hi"; rate(r,u) = T1[r][lo] T2[r][hi]).
+//
+// Row metadata shared by the three kernels below: for table row r of a product-form space
+//   kind 0: unused   1: event absent in this patient (or a diagnosis pseudo row)   2: event on lo bit `bit`
+//   3: event on hi bit `bit`
+struct PfRows { int8_t kind[NR], bit[NR]; };
+__device__ __forceinline__ void pf_rows_build(PfRows& m, const SpaceDev& sp, int t)
 {
-    const uint32_t wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if ((wg >> 2) >= count) return;
-    const int rg = wg & 3;
-    const Item it = items[wg >> 2];                     // a = chunk of 32 lo, b = hi slice
+    if (t >= NR) return;
+    const int K1 = sp.splitA;
+    const SetupSel sel = setup_sel(sp, 0);
+    int kind = t < sel.nrows ? 1 : 0, bit = 0;
+    if ((t == ROW_DP || t == ROW_DM) && sel.dg == 4) kind = 1;
+    if (t < sel.nrows)
+        for (int b = 0; b < sp.KA; ++b)
+            if (sp.evA[b] == t) { kind = b < K1 ? 2 : 3; bit = b < K1 ? b : b - K1; }
+    m.kind[t] = (int8_t)kind; m.bit[t] = (int8_t)bit;
+}
+
+// Diagonal of a product-form space (replaces the per-state 26-term loop of the first version):
+//   D[hi][lo] = d(u) + sum_{r not in u} T1[r][lo] T2[r][hi]
+// is a rank-(nrows+2) product once the rows of present events are masked on their own bit; d(u) is 1
+// (diagnosis_theta form, vanilla.py:269) or, for type 2, the two diagnosis-rate products held in rows 30/31.
+// CTA = 16 hi x 128 lo, thread = 2 hi x 4 lo.   item: a = lo block, b = hi block
+__global__ void __launch_bounds__(256)
+k_diag_prod(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, double* __restrict__ S)
+{
+    __shared__ PfRows rows;
+    const Item it = items[blockIdx.x];
     const SpaceDev& sp = spaces[it.space];
+    pf_rows_build(rows, sp, threadIdx.x);
+    __syncthreads();
+    const int K1 = sp.splitA, K2 = sp.KA - K1;
+    const uint32_t N1 = 1u << K1, N2 = 1u << K2;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t lo0 = (it.a << 7) | ((uint32_t)lane << 2);
+    const uint32_t hi0 = (it.b << 4) | ((uint32_t)w << 1);
+    if (lo0 >= N1 || hi0 >= N2) return;
+    const double* T1 = S + sp.tabA;
+    const double* T2 = T1 + ((uint64_t)NR << K1);
+    double* vec = S + sp.tabA + ((uint64_t)NR << K1) + ((uint64_t)NR << K2);
+    const bool s2 = setup_sel(sp, 0).dg == 4;
+    double d[2][4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) d[h][t] = s2 ? 0.0 : 1.0;
+    for (int r = 0; r < NR; ++r) {
+        const int kind = rows.kind[r];
+        if (kind == 0 || r >= ROW_D) continue;
+        double b[4];
+        ld4(T1 + ((uint64_t)r << K1) + lo0, b);
+        double a0 = T2[((uint64_t)r << K2) + hi0], a1 = T2[((uint64_t)r << K2) + hi0 + 1];
+        const int bit = rows.bit[r];
+        if (kind == 2) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) if (((lo0 + t) >> bit) & 1u) b[t] = 0.0;
+        } else if (kind == 3) {
+            if ((hi0 >> bit) & 1u) a0 = 0.0;
+            if (((hi0 + 1) >> bit) & 1u) a1 = 0.0;
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { d[0][t] = fma(a0, b[t], d[0][t]); d[1][t] = fma(a1, b[t], d[1][t]); }
+    }
+    const uint64_t NG = (uint64_t)N1 << K2;
+    if (s2) {
+        double bp[4], bm[4];
+        ld4(T1 + ((uint64_t)ROW_DP << K1) + lo0, bp);
+        ld4(T1 + ((uint64_t)ROW_DM << K1) + lo0, bm);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const double ap = T2[((uint64_t)ROW_DP << K2) + hi0 + h], am = T2[((uint64_t)ROW_DM << K2) + hi0 + h];
+            const uint64_t u0 = ((uint64_t)(hi0 + h) << K1) | lo0;
+            double vp[4], vm[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { vp[t] = ap * bp[t]; vm[t] = am * bm[t]; d[h][t] += vp[t] + vm[t]; }
+            st4(vec + NG + u0, vp[0], vp[1], vp[2], vp[3]);
+            st4(vec + 2 * NG + u0, vm[0], vm[1], vm[2], vm[3]);
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) st4(vec + (((uint64_t)(hi0 + h) << K1) | lo0), d[h][0], d[h][1], d[h][2], d[h][3]);
+}
+
+// Weighted marginals of a product-form space.  With x the adjoint and y the forward vector, row r of the gradient
+// needs  sum_u T1[r][lo] T2[r][hi] E_r(u) [b in u]  with
+//     E_r(u) = -x(u) y(u)                          event r absent in this patient (and the diagnosis pseudo rows)
+//            = [a not in u] y(u) (x(u + a) - x(u))  event r sits on bit a
+// (vanilla.py:328-393 spends n_tot x_partial_Q_y passes on this).  Summing out hi first and lo first gives
+//     H1[r][lo] = sum_hi T2[r][hi] E_r(hi,lo)        H2[r][hi] = sum_lo T1[r][lo] E_r(hi,lo)
+// and k_finish folds T1 H1 over the lo bits, T2 H2 over the hi bits.  A lane owns four consecutive lo (32-byte
+// loads), a warp eight table rows, the four warps of a CTA the 32 rows.
+// Output (stP): slices x (NR + KA) x N1 partial H1 tables, then (NR + KA) x N2 for H2 (rows >= NR unused).
+__device__ __forceinline__ void pf_E(int kind, int bit, uint32_t hi, uint32_t lo0, int K1, const double* __restrict__ x,
+                                     const double (&xv)[4], const double (&yv)[4], const double (&ng)[4], double (&e)[4], bool& zero)
+{
+    zero = false;
+    if (kind == 1) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) e[t] = ng[t];
+        return;
+    }
+    if (kind == 2) {
+        if (bit == 0) {
+            e[0] = yv[0] * (xv[1] - xv[0]); e[1] = 0.0; e[2] = yv[2] * (xv[3] - xv[2]); e[3] = 0.0;
+        } else if (bit == 1) {
+            e[0] = yv[0] * (xv[2] - xv[0]); e[1] = yv[1] * (xv[3] - xv[1]); e[2] = 0.0; e[3] = 0.0;
+        } else {
+            if ((lo0 >> bit) & 1u) { zero = true; return; }
+            double xa[4];
+            ld4(x + (((uint64_t)hi << K1) | (lo0 | (1u << bit))), xa);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) e[t] = yv[t] * (xa[t] - xv[t]);
+        }
+        return;
+    }
+    if ((hi >> bit) & 1u) { zero = true; return; }
+    double xa[4];
+    ld4(x + (((uint64_t)(hi | (1u << bit)) << K1) | lo0), xa);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) e[t] = yv[t] * (xa[t] - xv[t]);
+}
+
+// item: a = block of 128 lo, b = hi slice
+__global__ void __launch_bounds__(128, 4)
+k_pf_lo(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, double* __restrict__ S)
+{
+    __shared__ PfRows rows;
+    const Item it = items[blockIdx.x];
+    const SpaceDev& sp = spaces[it.space];
+    pf_rows_build(rows, sp, threadIdx.x);
+    __syncthreads();
     const int KA = sp.KA, K1 = sp.splitA, K2 = KA - K1;
     const uint32_t N1 = 1u << K1, N2 = 1u << K2;
-    const uint32_t lo = (it.a << 5) | lane;
-    const bool valid = lo < N1;
+    const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const uint32_t lo0 = (it.a << 7) | ((uint32_t)lane << 2);
+    if (lo0 >= N1) return;
     const uint32_t per = (N2 + sp.slices - 1) / sp.slices;
     const uint32_t h0 = it.b * per, h1 = min(N2, h0 + per);
     const double* x = S + sp.x_off;
     const double* y = S + sp.y_off;
     const double* T2 = S + sp.tabA + ((uint64_t)NR << K1);
-    constexpr int NBIT = (MB + PF_RG - 1) / PF_RG;
-    double aR[PF_ROWS], aC[NBIT];
+    int kind[8], bit[8];
 #pragma unroll
-    for (int r = 0; r < PF_ROWS; ++r) aR[r] = 0.0;
+    for (int j = 0; j < 8; ++j) { kind[j] = rows.kind[rg * 8 + j]; bit[j] = rows.bit[rg * 8 + j]; }
+    double acc[8][4];
 #pragma unroll
-    for (int a = 0; a < NBIT; ++a) aC[a] = 0.0;
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) acc[j][t] = 0.0;
     for (uint32_t hi = h0; hi < h1; ++hi) {
-        const uint32_t u = (hi << K1) | lo;
-        const double xv = valid ? x[u] : 0.0, yv = valid ? y[u] : 0.0;
-        const double g = xv * yv;
+        const uint64_t u0 = ((uint64_t)hi << K1) | lo0;
+        double xv[4], yv[4], ng[4];
+        ld4(x + u0, xv);
+        ld4(y + u0, yv);
 #pragma unroll
-        for (int r = 0; r < PF_ROWS; ++r) aR[r] = fma(T2[((uint64_t)(rg * PF_ROWS + r) << K2) + hi], g, aR[r]);
+        for (int t = 0; t < 4; ++t) ng[t] = -(xv[t] * yv[t]);
 #pragma unroll
-        for (int q = 0; q < NBIT; ++q) {
-            const int a = q * PF_RG + rg;
-            if (a < KA) {
-                const uint32_t bit = 1u << a;
-                double xa = 0.0;
-                if (a < 5) xa = __shfl_xor_sync(0xffffffffu, xv, 1 << a);
-                const bool has = (u >> a) & 1u;
-                if (a >= 5 && valid && !has) xa = x[u | bit];
-                const double c = has ? g : yv * xa;
-                aC[q] = fma(T2[((uint64_t)sp.evA[a] << K2) + hi], c, aC[q]);
-            }
+        for (int j = 0; j < 8; ++j) {
+            if (kind[j] == 0) continue;
+            double e[4];
+            bool zero;
+            pf_E(kind[j], bit[j], hi, lo0, K1, x, xv, yv, ng, e, zero);
+            if (zero) continue;
+            const double tw = T2[((uint64_t)(rg * 8 + j) << K2) + hi];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) acc[j][t] = fma(tw, e[t], acc[j][t]);
         }
     }
-    if (!valid) return;
     double* out = S + sp.stP + (uint64_t)it.b * (NR + KA) * N1;
 #pragma unroll
-    for (int r = 0; r < PF_ROWS; ++r) out[(uint64_t)(rg * PF_ROWS + r) * N1 + lo] = aR[r];
-#pragma unroll
-    for (int q = 0; q < NBIT; ++q) { const int a = q * PF_RG + rg; if (a < KA) out[(uint64_t)(NR + a) * N1 + lo] = aC[q]; }
+    for (int j = 0; j < 8; ++j) st4(out + (uint64_t)(rg * 8 + j) * N1 + lo0, acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
 }
 
-template <int MB>
-__global__ void __launch_bounds__(256)
-k_pfin_hi(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, uint32_t count, double* __restrict__ S)
+// item: a = block of PF_HB hi
+constexpr int PF_HB = 4;
+__global__ void __launch_bounds__(128, 4)
+k_pf_hi(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, double* __restrict__ S)
 {
-    const uint32_t wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if ((wg >> 2) >= count) return;
-    const int rg = wg & 3;
-    const Item it = items[wg >> 2];                     // a = hi
+    __shared__ PfRows rows;
+    __shared__ double red[4][8 * PF_HB][33];
+    const Item it = items[blockIdx.x];
     const SpaceDev& sp = spaces[it.space];
+    pf_rows_build(rows, sp, threadIdx.x);
+    __syncthreads();
     const int KA = sp.KA, K1 = sp.splitA, K2 = KA - K1;
     const uint32_t N1 = 1u << K1, N2 = 1u << K2;
-    const uint32_t hi = it.a;
+    const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const uint32_t hb = it.a * PF_HB;
     const double* x = S + sp.x_off;
     const double* y = S + sp.y_off;
     const double* T1 = S + sp.tabA;
-    constexpr int NBIT = (MB + PF_RG - 1) / PF_RG;
-    double aR[PF_ROWS], aC[NBIT];
+    int kind[8], bit[8];
 #pragma unroll
-    for (int r = 0; r < PF_ROWS; ++r) aR[r] = 0.0;
+    for (int j = 0; j < 8; ++j) { kind[j] = rows.kind[rg * 8 + j]; bit[j] = rows.bit[rg * 8 + j]; }
+    double acc[8][PF_HB];
 #pragma unroll
-    for (int a = 0; a < NBIT; ++a) aC[a] = 0.0;
-    for (uint32_t l0 = 0; l0 < N1; l0 += 32) {
-        const uint32_t lo = l0 + lane;
-        const bool valid = lo < N1;
-        const uint32_t u = (hi << K1) | lo;
-        const double xv = valid ? x[u] : 0.0, yv = valid ? y[u] : 0.0;
-        const double g = xv * yv;
+    for (int j = 0; j < 8; ++j)
 #pragma unroll
-        for (int r = 0; r < PF_ROWS; ++r) aR[r] = fma(valid ? T1[((uint64_t)(rg * PF_ROWS + r) << K1) + lo] : 0.0, g, aR[r]);
+        for (int h = 0; h < PF_HB; ++h) acc[j][h] = 0.0;
+    for (uint32_t lo0 = (uint32_t)lane << 2; lo0 < N1; lo0 += 128) {
 #pragma unroll
-        for (int q = 0; q < NBIT; ++q) {
-            const int a = q * PF_RG + rg;
-            if (a < KA) {
-                const uint32_t bit = 1u << a;
-                double xa = 0.0;
-                if (a < 5) xa = __shfl_xor_sync(0xffffffffu, xv, 1 << a);
-                const bool has = (u >> a) & 1u;
-                if (a >= 5 && valid && !has) xa = x[u | bit];
-                const double c = has ? g : yv * xa;
-                aC[q] = fma(valid ? T1[((uint64_t)sp.evA[a] << K1) + lo] : 0.0, c, aC[q]);
+        for (int h = 0; h < PF_HB; ++h) {
+            const uint32_t hi = hb + h;
+            if (hi >= N2) continue;
+            const uint64_t u0 = ((uint64_t)hi << K1) | lo0;
+            double xv[4], yv[4], ng[4];
+            ld4(x + u0, xv);
+            ld4(y + u0, yv);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) ng[t] = -(xv[t] * yv[t]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (kind[j] == 0) continue;
+                double e[4];
+                bool zero;
+                pf_E(kind[j], bit[j], hi, lo0, K1, x, xv, yv, ng, e, zero);
+                if (zero) continue;
+                double tv[4];
+                ld4(T1 + ((uint64_t)(rg * 8 + j) << K1) + lo0, tv);
+                acc[j][h] = fma(tv[3], e[3], fma(tv[2], e[2], fma(tv[1], e[1], fma(tv[0], e[0], acc[j][h]))));
             }
         }
     }
+    // sum over the lanes through shared memory: value q of lane l -> red[q][l]; lane q then adds row q
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int h = 0; h < PF_HB; ++h) red[rg][j * PF_HB + h][lane] = acc[j][h];
+    __syncwarp();
+    double s = 0.0;
+#pragma unroll
+    for (int l = 0; l < 32; ++l) s += red[rg][lane][l];
+    const int j = lane / PF_HB, h = lane % PF_HB;
     double* out = S + sp.stP + (uint64_t)sp.slices * (NR + KA) * N1;
-#pragma unroll
-    for (int r = 0; r < PF_ROWS; ++r) { const double t = warp_sum(aR[r]); if (lane == 0) out[(uint64_t)(rg * PF_ROWS + r) * N2 + hi] = t; }
-#pragma unroll
-    for (int q = 0; q < NBIT; ++q) {
-        const int a = q * PF_RG + rg;
-        if (a < KA) { const double t = warp_sum(aC[q]); if (lane == 0) out[(uint64_t)(NR + a) * N2 + hi] = t; }
-    }
+    if (hb + h < N2) out[(uint64_t)(rg * 8 + j) * N2 + hb + h] = s;
 }
-
 // ------------------------------------------------------------------------------------------
 // Gradient contraction.  For event row i and sub-state u of a group (i not in u)
 //     w_i(u) = T[i][u] * E_i(u),   E_i(u) = sum_other y (x[u + i] - x[u])   (i is a bit of the group)
@@ -1390,13 +1509,10 @@ k_finish(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, ui
                     const bool rrow = r < nrows, rps = (r == ROW_DP || r == ROW_DM) && has_pseudo;
                     double wv = 0.0;
                     if (uv && (rrow || rps)) {
-                        if (pmode) {
-                            double hsum = 0.0, csum = 0.0;
-                            for (int q = 0; q < psl; ++q) {
-                                hsum += pH[q * pslice + (uint64_t)r * NG + u];
-                                if (rrow && rb >= 0) csum += pH[q * pslice + (uint64_t)(NR + rb) * NG + u];
-                            }
-                            wv = ptab[(uint64_t)r * NG + u] * (csum - hsum);
+                        if (pmode) {                              // weighted marginals from k_pf_lo / k_pf_hi
+                            double hsum = 0.0;
+                            for (int q = 0; q < psl; ++q) hsum += pH[q * pslice + (uint64_t)r * NG + u];
+                            wv = ptab[(uint64_t)r * NG + u] * hsum;
                         } else {
                             const double R = rrow ? sd.rate(r, u) : sd.special(r, u);
                             double E = -gg;
