@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmetmhn_b200.so")
+LIB_PATH = os.environ.get("MMH_LIB") or os.path.join(_HERE, "libmetmhn_b200.so")   # MMH_LIB: A/B builds of the same library
 
 MMH_OK, MMH_EINVAL, MMH_ECUDA, MMH_ENOMEM, MMH_ETOOLARGE = 0, -1, -2, -3, -4
 MAX_MUT = 28

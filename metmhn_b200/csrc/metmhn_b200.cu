@@ -15,6 +15,7 @@
 using namespace mmh;
 
 static constexpr int RED_SLICES = 32;            // first stage of the gradient-partials reduction
+static constexpr size_t RB_SMEM = (size_t)RB_STATES * sizeof(double);
 static constexpr size_t FIN_SMEM = (size_t)(NACC * NR * NR + FIN_WARPS * NR * 33) * sizeof(double);
 
 static thread_local std::string g_err;
@@ -39,6 +40,7 @@ struct ChunkPlan {
     bool wide = false;                           // some group has more than MAXT bits
     std::vector<Range> main_lv, sec_lv;          // big-tier segments per popcount level (generic kernel)
     std::vector<Range> main_lvt, sec_lvt;        // big-tier tiles per level (tiled kernel)
+    std::vector<Range> main_lvr, sec_lvr;        // big-tier row blocks per row level (row-block kernel)
     uint64_t scratch = 0;                        // doubles
 };
 
@@ -119,7 +121,7 @@ static uint64_t space_scratch(SpaceDev& s, uint64_t off)
     } else if (s.kind != K_PRE && s.splitA) {
         // product-form gradient: weighted marginals over the low / high part (k_pfin_lo / k_pfin_hi)
         const uint64_t N1 = 1ull << s.splitA, N2 = 1ull << (s.KA - s.splitA);
-        s.slices = (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(1, N2 / 64));
+        s.slices = (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(1, N2 / 8));
         s.stP = take((uint64_t)s.slices * (NR + s.KA) * N1 + (uint64_t)(NR + s.KA) * N2);
     }
     return off;
@@ -361,6 +363,11 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
             if (s.kind == K_JOINT) return !s.splitA && !s.splitB && s.KA >= 4;
             return s.splitA >= 4;
         };
+        // experimental (profiles/NOTES.md): the row-block kernel is only used when MMH_ROWBLOCK=1
+        static const bool use_rowblock = [] { const char* e = std::getenv("MMH_ROWBLOCK"); return e && std::atoi(e) != 0; }();
+        auto rowblock = [&](const SpaceDev& s) {
+            return use_rowblock && tiled(s) && (s.kind == K_JOINT ? s.KA : s.splitA) <= RB_MAXKC;
+        };
         auto levels_of = [&](auto pred, std::vector<Range>& lv) {
             int maxkh = -1;
             for (uint32_t i = 0; i < ck.nspaces; ++i) if (pred(sp[i]) && bits(sp[i]) >= BIGK && !tiled(sp[i])) maxkh = std::max(maxkh, bits(sp[i]) - 7);
@@ -389,7 +396,7 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
                 else { kbA = s.splitA - 4; kbB = s.KA - s.splitA; }
             };
             for (uint32_t i = 0; i < ck.nspaces; ++i)
-                if (pred(sp[i]) && tiled(sp[i])) { int a, b; dims(sp[i], a, b); maxl = std::max(maxl, a + b); }
+                if (pred(sp[i]) && tiled(sp[i]) && !rowblock(sp[i])) { int a, b; dims(sp[i], a, b); maxl = std::max(maxl, a + b); }
             if (maxl < 0) return;
             lv.resize(maxl + 1);
             for (int l = 0; l <= maxl; ++l) {
@@ -400,7 +407,7 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
                 for (int pass = 0; pass < 2; ++pass) {
                     const uint64_t per_cta = total <= 8ull * 3 * 148 ? 8 : total <= 16ull * 3 * 148 ? 16 : TILES_PER_CTA;
                     for (uint32_t i = 0; i < ck.nspaces; ++i) {
-                        if (!pred(sp[i]) || !tiled(sp[i])) continue;
+                        if (!pred(sp[i]) || !tiled(sp[i]) || rowblock(sp[i])) continue;
                         int kbA, kbB;
                         dims(sp[i], kbA, kbB);
                         if (l > kbA + kbB) continue;
@@ -419,10 +426,39 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
                 lv[l].cnt = (uint32_t)(items.size() - lv[l].off);
             }
         };
+        // row-block kernel: one launch per ROW level; an item is up to RB_STATES >> KC rows of that level
+        auto levels_of_r = [&](auto pred, std::vector<Range>& lv) {
+            int maxl = -1;
+            auto dims = [&](const SpaceDev& s, int& kc, int& kr) {
+                if (s.kind == K_JOINT) { kc = s.KA; kr = s.KB; }
+                else { kc = s.splitA; kr = s.KA - s.splitA; }
+            };
+            for (uint32_t i = 0; i < ck.nspaces; ++i)
+                if (pred(sp[i]) && rowblock(sp[i])) { int kc, kr; dims(sp[i], kc, kr); maxl = std::max(maxl, kr); }
+            if (maxl < 0) return;
+            lv.resize(maxl + 1);
+            for (int l = 0; l <= maxl; ++l) {
+                lv[l].off = items.size();
+                for (uint32_t i = 0; i < ck.nspaces; ++i) {
+                    if (!pred(sp[i]) || !rowblock(sp[i])) continue;
+                    int kc, kr;
+                    dims(sp[i], kc, kr);
+                    if (l > kr) continue;
+                    need_hs(kc - 4); need_hs(kr);
+                    const uint32_t nB = hs_lvl[kr][l + 1] - hs_lvl[kr][l];
+                    const uint32_t rmax = std::max<uint32_t>(1u, (uint32_t)RB_STATES >> kc);
+                    for (uint32_t r0 = 0; r0 < nB; r0 += rmax)
+                        items.push_back({i, (uint32_t)l | (std::min<uint32_t>(rmax, nB - r0) << 8), r0});
+                }
+                lv[l].cnt = (uint32_t)(items.size() - lv[l].off);
+            }
+        };
         levels_of(is_main, ck.main_lv);
         levels_of(is_sec, ck.sec_lv);
         levels_of_t(is_main, ck.main_lvt);
         levels_of_t(is_sec, ck.sec_lvt);
+        levels_of_r(is_main, ck.main_lvr);
+        levels_of_r(is_sec, ck.sec_lvr);
         ck.st_a.off = items.size();
         for (uint32_t i = 0; i < ck.nspaces; ++i)
             if (sp[i].kind == K_JOINT) {
@@ -523,6 +559,8 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
+    CK(cudaFuncSetAttribute(k_solve_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
+    CK(cudaFuncSetAttribute(k_solve_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
     CK(cudaFuncSetAttribute(k_finish<MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIN_SMEM));
     CK(cudaFuncSetAttribute(k_finish<MAXG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIN_SMEM));
     h->st.scratch_bytes = (double)max_scratch * 8.0 * h->ns;
@@ -603,6 +641,16 @@ static int enqueue_eval(mmh_handle* h, const double* d_params, double w0, double
                 ++launches;
             }
         };
+        auto bigr = [&](const std::vector<Range>& lv, bool adj) {
+            const int L = (int)lv.size();
+            for (int q = 0; q < L; ++q) {
+                const Range& r = lv[adj ? L - 1 - q : q];
+                if (!r.cnt) continue;
+                if (adj) k_solve_rows<true><<<r.cnt, RB_THREADS, RB_SMEM, st>>>(sp, h->d_items + r.off, h->d_hs, h->d_hsidx, S);
+                else     k_solve_rows<false><<<r.cnt, RB_THREADS, RB_SMEM, st>>>(sp, h->d_items + r.off, h->d_hs, h->d_hsidx, S);
+                ++launches;
+            }
+        };
         tick(0);
         k_setup<<<ck.setup.cnt, 256, 0, st>>>(sp, h->d_items + ck.setup.off, h->d_par, S); ++launches;
         if (ck.setup_wide.cnt) { k_setup_wide<<<ck.setup_wide.cnt, 1024, 0, st>>>(sp, h->d_items + ck.setup_wide.off, h->d_par, S); ++launches; }
@@ -610,15 +658,15 @@ static int enqueue_eval(mmh_handle* h, const double* d_params, double w0, double
         tick(1);
         small(ck.pre, false); small4(ck.pre4, false);
         small(ck.main_small, false); small4(ck.main_small4, false);
-        big(ck.main_lv, false); bigt(ck.main_lvt, false);
+        big(ck.main_lv, false); bigt(ck.main_lvt, false); bigr(ck.main_lvr, false);
         small(ck.sec_small, false); small4(ck.sec_small4, false);
-        big(ck.sec_lv, false); bigt(ck.sec_lvt, false);
+        big(ck.sec_lv, false); bigt(ck.sec_lvt, false); bigr(ck.sec_lvr, false);
         tick(5);
         if (ck.logp.cnt) { k_logp<<<(ck.logp.cnt + 127) / 128, 128, 0, st>>>(sp, h->d_lists + ck.logp.off, ck.logp.cnt, S, h->d_logp); ++launches; }
         if (!want_grad) continue;
         tick(2);
         small(ck.sec_small, true); small4(ck.sec_small4, true);
-        big(ck.sec_lv, true); bigt(ck.sec_lvt, true);
+        big(ck.sec_lv, true); bigt(ck.sec_lvt, true); bigr(ck.sec_lvr, true);
         tick(5);
         if (ck.joints.cnt) {
             k_direct<<<(ck.joints.cnt + 255) / 256, 256, 0, st>>>(sp, h->d_lists + ck.joints.off, ck.joints.cnt, S, d_tdir);
@@ -627,7 +675,7 @@ static int enqueue_eval(mmh_handle* h, const double* d_params, double w0, double
         }
         tick(2);
         small(ck.main_small, true); small4(ck.main_small4, true);
-        big(ck.main_lv, true); bigt(ck.main_lvt, true);
+        big(ck.main_lv, true); bigt(ck.main_lvt, true); bigr(ck.main_lvr, true);
         small(ck.pre, true); small4(ck.pre4, true);
         tick(3);
         if (ck.st_a.cnt) {

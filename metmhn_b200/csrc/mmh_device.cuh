@@ -711,6 +711,9 @@ k_solve_big4(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs,
 // popcount lB and share the column block cA (popcount lA), so every loop of the warp has a uniform trip count and
 // the column-rate loads of the 8 row groups hit the same line.  One launch per level lA + lB.
 constexpr int TILES_PER_CTA = 32;
+#ifndef TILE_CTAS
+#define TILE_CTAS 3
+#endif
 
 struct TileCtx {
     const double* colA[MAXG];          // column bit q: column factor of its rate (T_A[ev] or T1[ev])
@@ -761,17 +764,12 @@ __device__ __forceinline__ void st4(double* __restrict__ p, double a, double b, 
     asm volatile("st.global.v4.f64 [%4], {%0,%1,%2,%3};" :: "d"(a), "d"(b), "d"(c), "d"(d), "l"(p) : "memory");
 }
 
-template <bool ADJ, bool PROD>
-__device__ __forceinline__ void solve_tile16(const SpaceDev& sp, const SpaceDev* __restrict__ spaces, const TileCtx& c,
-                                             double* __restrict__ S, uint32_t cA, uint32_t row, bool valid, int lane)
+// right-hand side of the four states of a lane: non-zero on few states only (except the second phase's start vector)
+template <bool ADJ>
+__device__ __forceinline__ void tile_rhs(const SpaceDev& sp, const SpaceDev* __restrict__ spaces, const double* __restrict__ S,
+                                         int KC, int KR, uint32_t row, uint32_t lo0, double (&acc)[4])
 {
-    const int KC = c.KC, KR = c.KR;
-    const int lc = lane & 3;
-    const uint32_t lo0 = (cA << 4) | ((uint32_t)lc << 2);
     const uint32_t s0 = (row << KC) | lo0;
-    double* v = S + (ADJ ? sp.x_off : sp.y_off);
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    // ---- right-hand side: non-zero on few states only (except the second phase's start vector) ----
     {
         const uint32_t NC = 1u << KC, NRW = 1u << KR;
         bool any;
@@ -788,37 +786,14 @@ __device__ __forceinline__ void solve_tile16(const SpaceDev& sp, const SpaceDev*
             for (int t = 0; t < 4; ++t) acc[t] = ADJ ? rhs_adj(sp, spaces, S, s0 + t) : rhs_fwd(sp, spaces, S, s0 + t);
         }
     }
-    // Edges are taken NB at a time, all loads of a round before its FMAs: a tile is a chain of dependent rounds and
-    // thin levels have no other warps to hide the memory latency behind.
-    // ---- column bits >= 4 (uniform over the warp): FWD visits the set bits of cA, ADJ the unset ones ----
-    {
-        constexpr int NB = 2;
-        uint32_t m = ADJ ? (~cA & ((1u << (KC - 4)) - 1u)) : cA;
-        while (m) {
-            double r[NB][4], y[NB][4], k[NB];
-#pragma unroll
-            for (int q = 0; q < NB; ++q) {
-                const bool on = m != 0u;
-                const int a = on ? __ffs(m) + 3 : 4;
-                m &= m - 1;
-                const uint32_t bit = 1u << a;
-                k[q] = 1.0;
-                if (on) {
-                    ld4(c.colA[a] + (ADJ ? lo0 : (lo0 ^ bit)), r[q]);
-                    ld4(v + (s0 ^ bit), y[q]);
-                    if (PROD) k[q] = c.rowA[a][row];
-                } else {
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) { r[q][t] = 0.0; y[q][t] = 0.0; }
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < NB; ++q)
-#pragma unroll
-                for (int t = 0; t < 4; ++t) acc[t] = fma(PROD ? r[q][t] * k[q] : r[q][t], y[q][t], acc[t]);
-        }
-    }
-    // ---- row bits (same count in every row group of the warp) ----
+}
+
+// edges on the row bits of a lane's four states (sources in global memory): acc += rate * v[other row]
+template <bool ADJ, bool PROD>
+__device__ __forceinline__ void tile_row_edges(const TileCtx& c, const double* __restrict__ v, uint32_t row, uint32_t lo0,
+                                               double (&acc)[4])
+{
+    const int KC = c.KC, KR = c.KR;
     {
         constexpr int NB = 3;
         uint32_t m = ADJ ? (~row & ((1u << KR) - 1u)) : row;
@@ -855,6 +830,15 @@ __device__ __forceinline__ void solve_tile16(const SpaceDev& sp, const SpaceDev*
             }
         }
     }
+}
+
+// diagonal, column bits 0,1 (inside the lane) and 2,3 (across the four lanes of a row group): acc -> val
+template <bool ADJ, bool PROD>
+__device__ __forceinline__ void tile_tail(const TileCtx& c, uint32_t row, uint32_t lo0, int lane, double (&acc)[4], double (&val)[4])
+{
+    const int KC = c.KC;
+    const int lc = lane & 3;
+    const uint32_t s0 = (row << KC) | lo0;
     // ---- diagonal ----
     double inv[4];
     {
@@ -911,7 +895,6 @@ __device__ __forceinline__ void solve_tile16(const SpaceDev& sp, const SpaceDev*
             for (int t = 0; t < 4; ++t) { w1a[t] *= k2; w1b[t] *= k3; }
         }
     }
-    double val[4];
     auto fin = [&]() {
         if (!ADJ) {
             val[0] = acc[0] * inv[0];
@@ -940,12 +923,58 @@ __device__ __forceinline__ void solve_tile16(const SpaceDev& sp, const SpaceDev*
         acc[t] = fma(w1b[t], q, fma(w1a[t], p, acc[t]));
     }
     fin();
+}
+
+template <bool ADJ, bool PROD>
+__device__ __forceinline__ void solve_tile16(const SpaceDev& sp, const SpaceDev* __restrict__ spaces, const TileCtx& c,
+                                             double* __restrict__ S, uint32_t cA, uint32_t row, bool valid, int lane)
+{
+    const int KC = c.KC, KR = c.KR;
+    const int lc = lane & 3;
+    const uint32_t lo0 = (cA << 4) | ((uint32_t)lc << 2);
+    const uint32_t s0 = (row << KC) | lo0;
+    double* v = S + (ADJ ? sp.x_off : sp.y_off);
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    tile_rhs<ADJ>(sp, spaces, S, KC, KR, row, lo0, acc);
+    // Edges are taken NB at a time, all loads of a round before its FMAs: a tile is a chain of dependent rounds and
+    // thin levels have no other warps to hide the memory latency behind.
+    // ---- column bits >= 4 (uniform over the warp): FWD visits the set bits of cA, ADJ the unset ones ----
+    {
+        constexpr int NB = 2;
+        uint32_t m = ADJ ? (~cA & ((1u << (KC - 4)) - 1u)) : cA;
+        while (m) {
+            double r[NB][4], y[NB][4], k[NB];
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+                const bool on = m != 0u;
+                const int a = on ? __ffs(m) + 3 : 4;
+                m &= m - 1;
+                const uint32_t bit = 1u << a;
+                k[q] = 1.0;
+                if (on) {
+                    ld4(c.colA[a] + (ADJ ? lo0 : (lo0 ^ bit)), r[q]);
+                    ld4(v + (s0 ^ bit), y[q]);
+                    if (PROD) k[q] = c.rowA[a][row];
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) { r[q][t] = 0.0; y[q][t] = 0.0; }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < NB; ++q)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) acc[t] = fma(PROD ? r[q][t] * k[q] : r[q][t], y[q][t], acc[t]);
+        }
+    }
+    tile_row_edges<ADJ, PROD>(c, v, row, lo0, acc);
+    double val[4];
+    tile_tail<ADJ, PROD>(c, row, lo0, lane, acc, val);
     if (valid) st4(v + s0, val[0], val[1], val[2], val[3]);
 }
 
 // item: space, a = lA | lB << 8 | tiles << 16, b = first tile; tile t -> column block t / nBg, row group t % nBg
 template <bool ADJ>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, TILE_CTAS)
 k_solve_tile(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs, const uint32_t* __restrict__ hs,
              const uint32_t* __restrict__ hsidx, double* __restrict__ S)
 {
@@ -971,6 +1000,129 @@ k_solve_tile(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs,
         if (prod) solve_tile16<ADJ, true>(sp, spaces, ctx, S, cA, row, valid, lane);
         else      solve_tile16<ADJ, false>(sp, spaces, ctx, S, cA, row, valid, lane);
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// Row-block solve (big tier, at most RB_MAXKC column bits).  A CTA owns R rows of one row level lB together with ALL
+// their columns, R * 2^KC <= RB_STATES values held in shared memory:
+//   phase 1  thread = four columns of a row: right-hand side plus every edge on a row bit (sources are rows finished
+//            by earlier launches; fully coalesced 32-byte loads, one scalar rate per edge for a pair)
+//   phase 2  the column lattice of the R rows is solved inside shared memory, level after level of the column-block
+//            index (__syncthreads between levels); a warp takes 8 (row, column block) units of 16 states, edges on
+//            column bits >= 4 read shared memory, bits 0..3 are resolved as in the tile kernel (tile_tail)
+// Against the tile kernel this removes the global reads of the column edges and needs one launch per ROW level only.
+constexpr int RB_STATES = 8192;
+constexpr int RB_MAXKC = 13;
+constexpr int RB_THREADS = 256;
+
+__device__ __forceinline__ bool rowblock_space(const SpaceDev& sp)
+{
+    if (!tiled_space(sp)) return false;
+    return (sp.kind == K_JOINT ? sp.KA : sp.splitA) <= RB_MAXKC;
+}
+
+template <bool ADJ, bool PROD>
+__device__ __forceinline__ void solve_rows(const SpaceDev& sp, const SpaceDev* __restrict__ spaces, const TileCtx& c,
+                                           double* __restrict__ S, const uint32_t* __restrict__ hs,
+                                           const uint32_t* __restrict__ hsidx, uint32_t lB, uint32_t first, uint32_t R,
+                                           double* __restrict__ Yt)
+{
+    const int KC = c.KC, KR = c.KR;
+    const uint32_t NC = 1u << KC;
+    const uint32_t offB = hsidx[KR * 32 + lB] + first;
+    double* v = S + (ADJ ? sp.x_off : sp.y_off);
+    // ---- phase 1 ----
+    const uint32_t total = R << KC;
+    for (uint32_t idx = threadIdx.x * 4u; idx < total; idx += RB_THREADS * 4u) {
+        const uint32_t r = idx >> KC, lo0 = idx & (NC - 1u);
+        const uint32_t row = hs[offB + r];
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        tile_rhs<ADJ>(sp, spaces, S, KC, KR, row, lo0, acc);
+        tile_row_edges<ADJ, PROD>(c, v, row, lo0, acc);
+        double2* o = reinterpret_cast<double2*>(Yt + idx);
+        o[0] = make_double2(acc[0], acc[1]);
+        o[1] = make_double2(acc[2], acc[3]);
+    }
+    __syncthreads();
+    // ---- phase 2 ----
+    const int kbA = KC - 4;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, lc = lane & 3;
+    for (int q = 0; q <= kbA; ++q) {
+        const int lA = ADJ ? kbA - q : q;
+        const uint32_t offA = hsidx[kbA * 32 + lA];
+        const uint32_t nA = hsidx[kbA * 32 + lA + 1] - offA;
+        const uint32_t units = nA * R;
+        for (uint32_t u0 = (uint32_t)w * 8u; u0 < units; u0 += (RB_THREADS / 32) * 8u) {
+            const uint32_t u = u0 + (uint32_t)(lane >> 2);
+            const bool valid = u < units;
+            const uint32_t uu = valid ? u : units - 1u;
+            const uint32_t iA = uu / R, r = uu - iA * R;
+            const uint32_t cA = hs[offA + iA];
+            const uint32_t row = hs[offB + r];
+            const uint32_t lo0 = (cA << 4) | ((uint32_t)lc << 2);
+            double* yr = Yt + ((size_t)r << KC);
+            double acc[4];
+            {
+                const double2* a2 = reinterpret_cast<const double2*>(yr + lo0);
+                const double2 p0 = a2[0], p1 = a2[1];
+                acc[0] = p0.x; acc[1] = p0.y; acc[2] = p1.x; acc[3] = p1.y;
+            }
+            // column bits >= 4: values from shared memory, rates from the column tables
+            uint32_t m = ADJ ? (~cA & ((1u << kbA) - 1u)) : cA;
+            constexpr int NB = 2;
+            while (m) {
+                double rr[NB][4], yy[NB][4], k[NB];
+#pragma unroll
+                for (int e = 0; e < NB; ++e) {
+                    const bool on = m != 0u;
+                    const int a = on ? __ffs(m) + 3 : 4;
+                    m &= m - 1;
+                    const uint32_t bit = 1u << a;
+                    k[e] = 1.0;
+                    if (on) {
+                        ld4(c.colA[a] + (ADJ ? lo0 : (lo0 ^ bit)), rr[e]);
+                        const double2* y2 = reinterpret_cast<const double2*>(yr + (lo0 ^ bit));
+                        const double2 p0 = y2[0], p1 = y2[1];
+                        yy[e][0] = p0.x; yy[e][1] = p0.y; yy[e][2] = p1.x; yy[e][3] = p1.y;
+                        if (PROD) k[e] = c.rowA[a][row];
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) { rr[e][t] = 0.0; yy[e][t] = 0.0; }
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < NB; ++e)
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) acc[t] = fma(PROD ? rr[e][t] * k[e] : rr[e][t], yy[e][t], acc[t]);
+            }
+            double val[4];
+            tile_tail<ADJ, PROD>(c, row, lo0, lane, acc, val);
+            if (valid) {
+                double2* o = reinterpret_cast<double2*>(yr + lo0);
+                o[0] = make_double2(val[0], val[1]);
+                o[1] = make_double2(val[2], val[3]);
+                st4(v + (((uint64_t)row << KC) | lo0), val[0], val[1], val[2], val[3]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// item: space, a = lB | rows << 8, b = first row of the item inside level lB
+template <bool ADJ>
+__global__ void __launch_bounds__(RB_THREADS, 3)
+k_solve_rows(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs, const uint32_t* __restrict__ hs,
+             const uint32_t* __restrict__ hsidx, double* __restrict__ S)
+{
+    extern __shared__ double Yt[];
+    __shared__ TileCtx ctx;
+    const Item sg = segs[blockIdx.x];
+    const SpaceDev& sp = spaces[sg.space];
+    tile_ctx_build(ctx, sp, S, threadIdx.x);
+    __syncthreads();
+    const uint32_t lB = sg.a & 255u, R = sg.a >> 8;
+    if (sp.kind != K_JOINT) solve_rows<ADJ, true>(sp, spaces, ctx, S, hs, hsidx, lB, sg.b, R, Yt);
+    else                    solve_rows<ADJ, false>(sp, spaces, ctx, S, hs, hsidx, lB, sg.b, R, Yt);
 }
 
 // per-patient log-likelihood (likelihood.py:316,350,384,405,438)

@@ -1,8 +1,6 @@
 # targeted full captures (indices from the launch list of the same build, profiles/NOTES.md)
 export MMH_GRAPH=0 MMH_STREAMS=1 EVALS=1 VALUE_ONLY=0
 cap() { # name regex skip count
-  ncu --set full --import-source on --clock-control none -k "regex:$2" -s $3 -c $4 -o gpurun_out/p11_$1 -f python scripts/quick_time.py 25 100000 > gpurun_out/p11_$1.log 2>&1
+  ncu --set full --import-source on --clock-control none -k "regex:$2" -s $3 -c $4 -o gpurun_out/p13_$1 -f python scripts/quick_time.py 25 100000 > gpurun_out/p13_$1.log 2>&1
 }
-cap solve 'k_solve_tile' 1321 22
-cap stats 'k_stats_a|k_stats_b' 40 2
-ls -la gpurun_out/
+cap rows 'k_solve_rows' 1000 16
