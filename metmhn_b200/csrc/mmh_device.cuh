@@ -714,6 +714,12 @@ constexpr int TILES_PER_CTA = 32;
 #ifndef TILE_CTAS
 #define TILE_CTAS 3
 #endif
+#ifndef TILE_NBA
+#define TILE_NBA 2            // column-bit edges in flight per round
+#endif
+#ifndef TILE_NBB
+#define TILE_NBB 3            // row-bit edges in flight per round
+#endif
 
 struct TileCtx {
     const double* colA[MAXG];          // column bit q: column factor of its rate (T_A[ev] or T1[ev])
@@ -795,7 +801,7 @@ __device__ __forceinline__ void tile_row_edges(const TileCtx& c, const double* _
 {
     const int KC = c.KC, KR = c.KR;
     {
-        constexpr int NB = 3;
+        constexpr int NB = TILE_NBB;
         uint32_t m = ADJ ? (~row & ((1u << KR) - 1u)) : row;
         while (m) {
             double y[NB][4], k[NB];
@@ -940,7 +946,7 @@ __device__ __forceinline__ void solve_tile16(const SpaceDev& sp, const SpaceDev*
     // thin levels have no other warps to hide the memory latency behind.
     // ---- column bits >= 4 (uniform over the warp): FWD visits the set bits of cA, ADJ the unset ones ----
     {
-        constexpr int NB = 2;
+        constexpr int NB = TILE_NBA;
         uint32_t m = ADJ ? (~cA & ((1u << (KC - 4)) - 1u)) : cA;
         while (m) {
             double r[NB][4], y[NB][4], k[NB];
