@@ -41,6 +41,7 @@ struct ChunkPlan {
     std::vector<Range> main_lv, sec_lv;          // big-tier segments per popcount level (generic kernel)
     std::vector<Range> main_lvt, sec_lvt;        // big-tier tiles per level (tiled kernel)
     std::vector<Range> main_lvr, sec_lvr;        // big-tier row blocks per row level (row-block kernel)
+    std::vector<Range> main_lvt_adj, main_lvt_adjb;  // adjoint pass of the main tiled spaces: plain / with fused B statistics
     uint64_t scratch = 0;                        // doubles
 };
 
@@ -86,6 +87,26 @@ struct mmh_handle {
     mmh_stats_t st{};
 };
 
+// pairs whose adjoint solve also produces the group-B statistics (k_solve_tile_adjb); needs splitA/splitB
+static bool fused_b(const SpaceDev& s)
+{
+    static const bool off = [] { const char* e = std::getenv("MMH_FUSE_B"); return e && std::atoi(e) == 0; }();
+    return !off && s.kind == K_JOINT && !s.splitA && !s.splitB && s.KA >= 4 && (int)s.KA + (int)s.KB >= BIGK;
+}
+// number of partial tables: per column-block level lA one per chunk of 32 column blocks; base[lA] = first slot
+static uint32_t adjb_slots(int kbA, uint32_t* base)
+{
+    uint32_t n = 0;
+    double c = 1.0;                                     // C(kbA, lA)
+    for (int lA = 0; lA <= kbA; ++lA) {
+        if (base) base[lA] = n;
+        const uint64_t nA = (uint64_t)(c + 0.5);
+        n += (uint32_t)std::max<uint64_t>(1, (nA + 31) / 32);
+        c = c * (kbA - lA) / (lA + 1);
+    }
+    return n;
+}
+
 static uint64_t space_scratch(SpaceDev& s, uint64_t off)
 {
     const uint64_t NA = 1ull << s.KA, NB = 1ull << s.KB, N = NA * NB;
@@ -114,6 +135,7 @@ static uint64_t space_scratch(SpaceDev& s, uint64_t off)
         const uint64_t capB = std::max<uint64_t>(8, (2ull << 20) / ((s.KB + 1) * NB));
         s.slices = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(256, capA), std::max<uint64_t>(1, NB / 128));
         s.slicesB = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(256, capB), std::max<uint64_t>(1, NA / 2048));
+        if (fused_b(s)) s.slicesB = adjb_slots(s.KA - 4, nullptr);     // one partial table per (lA, column chunk)
         s.stA = take((s.KA + 1) * NA);
         s.stB = take((s.KB + 1) * NB);
         s.stP = take((uint64_t)s.slices * (s.KA + 1) * NA);
@@ -453,9 +475,43 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
                 lv[l].cnt = (uint32_t)(items.size() - lv[l].off);
             }
         };
+        // adjoint pass with fused group-B statistics: CTA = G row groups x C column blocks of one (lA, lB) split
+        auto levels_of_adjb = [&](std::vector<Range>& lv) {
+            int maxl = -1;
+            for (uint32_t i = 0; i < ck.nspaces; ++i)
+                if (fused_b(sp[i]) && !rowblock(sp[i])) maxl = std::max(maxl, (int)sp[i].KA - 4 + (int)sp[i].KB);
+            if (maxl < 0) return;
+            lv.resize(maxl + 1);
+            for (int l = 0; l <= maxl; ++l) {
+                lv[l].off = items.size();
+                for (uint32_t i = 0; i < ck.nspaces; ++i) {
+                    if (!fused_b(sp[i]) || rowblock(sp[i])) continue;
+                    const int kbA = sp[i].KA - 4, kbB = sp[i].KB;
+                    if (l > kbA + kbB) continue;
+                    need_hs(kbA); need_hs(kbB);
+                    uint32_t base[MMH_MAX_BITS + 1];
+                    adjb_slots(kbA, base);
+                    for (int lA = std::max(0, l - kbB); lA <= std::min(kbA, l); ++lA) {
+                        const int lB = l - lA;
+                        const uint32_t nA = hs_lvl[kbA][lA + 1] - hs_lvl[kbA][lA];
+                        const uint32_t nB = hs_lvl[kbB][lB + 1] - hs_lvl[kbB][lB];
+                        const uint32_t nBg = (nB + 7) / 8;
+                        uint32_t C = 32;
+                        if (nA < 32) { C = 1; while (C < nA) C <<= 1; }
+                        const uint32_t G = 32 / C, nch = nA < 32 ? 1 : (nA + 31) / 32;
+                        for (uint32_t jB = 0; jB < nBg; jB += G)
+                            for (uint32_t k = 0; k < nch; ++k)
+                                items.push_back({i, (uint32_t)lA | ((uint32_t)lB << 8), jB, k | ((base[lA] + k) << 16)});
+                    }
+                }
+                lv[l].cnt = (uint32_t)(items.size() - lv[l].off);
+            }
+        };
         levels_of(is_main, ck.main_lv);
         levels_of(is_sec, ck.sec_lv);
         levels_of_t(is_main, ck.main_lvt);
+        levels_of_t([&](const SpaceDev& s) { return is_main(s) && !fused_b(s); }, ck.main_lvt_adj);
+        levels_of_adjb(ck.main_lvt_adjb);
         levels_of_t(is_sec, ck.sec_lvt);
         levels_of_r(is_main, ck.main_lvr);
         levels_of_r(is_sec, ck.sec_lvr);
@@ -478,7 +534,7 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
         ck.st_ar.cnt = (uint32_t)(items.size() - ck.st_ar.off);
         ck.st_b.off = items.size();
         for (uint32_t i = 0; i < ck.nspaces; ++i)
-            if (sp[i].kind == K_JOINT)
+            if (sp[i].kind == K_JOINT && !(fused_b(sp[i]) && !rowblock(sp[i])))
                 for (uint32_t sl = 0; sl < sp[i].slicesB; ++sl)
                     for (uint32_t u = 0; u < (1u << sp[i].KB); ++u) items.push_back({i, u, sl});
         ck.st_b.cnt = (uint32_t)(items.size() - ck.st_b.off);
@@ -675,12 +731,18 @@ static int enqueue_eval(mmh_handle* h, const double* d_params, double w0, double
         }
         tick(2);
         small(ck.main_small, true); small4(ck.main_small4, true);
-        big(ck.main_lv, true); bigt(ck.main_lvt, true); bigr(ck.main_lvr, true);
+        big(ck.main_lv, true); bigt(ck.main_lvt_adj, true); bigr(ck.main_lvr, true);
+        for (int q = (int)ck.main_lvt_adjb.size() - 1; q >= 0; --q) {
+            const Range& r = ck.main_lvt_adjb[q];
+            if (!r.cnt) continue;
+            k_solve_tile_adjb<<<r.cnt, 256, 0, st>>>(sp, h->d_items + r.off, h->d_hs, h->d_hsidx, S);
+            ++launches;
+        }
         small(ck.pre, true); small4(ck.pre4, true);
         tick(3);
         if (ck.st_a.cnt) {
             k_stats_a<<<(ck.st_a.cnt + 7) / 8, 256, 0, st>>>(sp, h->d_items + ck.st_a.off, ck.st_a.cnt, S);
-            k_stats_b<<<(ck.st_b.cnt + 7) / 8, 256, 0, st>>>(sp, h->d_items + ck.st_b.off, ck.st_b.cnt, S);
+            if (ck.st_b.cnt) k_stats_b<<<(ck.st_b.cnt + 7) / 8, 256, 0, st>>>(sp, h->d_items + ck.st_b.off, ck.st_b.cnt, S);
             k_stats_reduce<<<ck.st_ar.cnt, 1024, 0, st>>>(sp, h->d_items + ck.st_ar.off, S);
             launches += 3;
         }

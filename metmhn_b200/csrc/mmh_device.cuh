@@ -50,7 +50,7 @@ struct EvalPar {                     // recomputed from the parameter vector at 
     double dp[NR], dm[NR];
 };
 
-struct Item { uint32_t space, a, b; };
+struct Item { uint32_t space, a, b, c; };
 
 // A group's tables.  Narrow group (KG <= MAXT): one NR x NG table whose rows 29..31 hold the diagonal part
 // and the two diagnosis-rate tables.  Wide group: rate(i, u) = T1[i][u_lo] * T2[i][u_hi] (the rates are
@@ -1005,6 +1005,136 @@ k_solve_tile(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs,
         const uint32_t row = hs[offB + min(ri, nB - 1u)];
         if (prod) solve_tile16<ADJ, true>(sp, spaces, ctx, S, cA, row, valid, lane);
         else      solve_tile16<ADJ, false>(sp, spaces, ctx, S, cA, row, valid, lane);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Adjoint tile solve of a pair with the group-B marginal statistics fused in.  The adjoint pass already holds, for
+// every state s and every row bit b not in s, the value x[s + b]; with y[s] (one more 32-byte load) the lane adds
+//     stB[1+b][uB] += sum_uA y[s] x[s + b]      stB[0][uB] += sum_uA x[s] y[s]
+// which saves the separate k_stats_b pass (one more full read of x and y plus KB/2 re-reads of x through L2).
+// A CTA is G row groups x C column blocks (G C <= 32) of one (lA, lB) split: the per-tile sums are parked in shared
+// memory, added over the CTA's column blocks in a fixed order and written to the partial table `slot` of the space
+// (every row receives every slot exactly once, no atomics; k_stats_reduce adds the slots).
+// item: a = lA | lB << 8, b = first row group, c = column chunk k | slot << 16
+constexpr int ADJB_MAXE = 17;                       // g + up to 16 row bits (pairs with plain tables have KB <= MAXT)
+
+__device__ __forceinline__ double group4_sum(double v)
+{
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+}
+
+__global__ void __launch_bounds__(256, 3)
+k_solve_tile_adjb(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs, const uint32_t* __restrict__ hs,
+                  const uint32_t* __restrict__ hsidx, double* __restrict__ S)
+{
+    __shared__ TileCtx ctx;
+    __shared__ double pb[32][8][ADJB_MAXE];
+    const Item sg = segs[blockIdx.x];
+    const SpaceDev& sp = spaces[sg.space];
+    tile_ctx_build(ctx, sp, S, threadIdx.x);
+    for (int t = threadIdx.x; t < 32 * 8 * ADJB_MAXE; t += blockDim.x) (&pb[0][0][0])[t] = 0.0;
+    __syncthreads();
+    const TileCtx& c = ctx;
+    const int KC = c.KC, KR = c.KR;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, lc = lane & 3, lg = lane >> 2;
+    const uint32_t lA = sg.a & 255u, lB = (sg.a >> 8) & 255u;
+    const uint32_t kch = sg.c & 0xffffu, slot = sg.c >> 16;
+    const uint32_t offA = hsidx[(KC - 4) * 32 + lA], nA = hsidx[(KC - 4) * 32 + lA + 1] - offA;
+    const uint32_t offB = hsidx[KR * 32 + lB], nB = hsidx[KR * 32 + lB + 1] - offB;
+    const uint32_t nBg = (nB + 7u) >> 3;
+    uint32_t C = 32;                                   // column blocks per row group in this CTA
+    if (nA < 32u) { C = 1; while (C < nA) C <<= 1; }
+    const uint32_t G = 32u / C;
+    double* v = S + sp.x_off;
+    const double* yv = S + sp.y_off;
+    for (uint32_t q = w; q < 32u; q += 8) {
+        const uint32_t g = q / C, ci = q - g * C;
+        const uint32_t jB = sg.b + g, iA = kch * 32u + ci;
+        if (jB >= nBg || iA >= nA) continue;           // uniform over the warp
+        const uint32_t ri = jB * 8u + (uint32_t)lg;
+        const bool valid = ri < nB;
+        const uint32_t cA = hs[offA + iA];
+        const uint32_t row = hs[offB + min(ri, nB - 1u)];
+        const uint32_t lo0 = (cA << 4) | ((uint32_t)lc << 2);
+        const uint32_t s0 = (row << KC) | lo0;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0}, y4[4];
+        ld4(yv + s0, y4);
+        tile_rhs<true>(sp, spaces, S, KC, KR, row, lo0, acc);
+        // column bits >= 4
+        {
+            constexpr int NB = TILE_NBA;
+            uint32_t m = ~cA & ((1u << (KC - 4)) - 1u);
+            while (m) {
+                double r[NB][4], y[NB][4];
+#pragma unroll
+                for (int e = 0; e < NB; ++e) {
+                    const bool on = m != 0u;
+                    const int a = on ? __ffs(m) + 3 : 4;
+                    m &= m - 1;
+                    if (on) { ld4(c.colA[a] + lo0, r[e]); ld4(v + (s0 | (1u << a)), y[e]); }
+                    else {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) { r[e][t] = 0.0; y[e][t] = 0.0; }
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < NB; ++e)
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) acc[t] = fma(r[e][t], y[e][t], acc[t]);
+            }
+        }
+        // row bits: solve edge and statistic from the same loaded values
+        {
+            constexpr int NB = TILE_NBB;
+            uint32_t m = ~row & ((1u << KR) - 1u);
+            while (m) {
+                double y[NB][4], k[NB];
+                int bq[NB];
+#pragma unroll
+                for (int e = 0; e < NB; ++e) {
+                    const bool on = m != 0u;
+                    const int b = on ? __ffs(m) - 1 : 0;
+                    m &= m - 1;
+                    bq[e] = on ? b : -1;
+                    if (on) {
+                        k[e] = c.rowB[b][row];
+                        ld4(v + (((uint64_t)(row | (1u << b)) << KC) | lo0), y[e]);
+                    } else {
+                        k[e] = 0.0;
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) y[e][t] = 0.0;
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < NB; ++e) {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) acc[t] = fma(k[e], y[e][t], acc[t]);
+                    const double d = group4_sum(fma(y4[3], y[e][3], fma(y4[2], y[e][2], fma(y4[1], y[e][1], y4[0] * y[e][0]))));
+                    if (lc == 0 && bq[e] >= 0) pb[q][lg][1 + bq[e]] = d;
+                }
+            }
+        }
+        double val[4];
+        tile_tail<true, false>(c, row, lo0, lane, acc, val);
+        const double gsum = group4_sum(fma(y4[3], val[3], fma(y4[2], val[2], fma(y4[1], val[1], y4[0] * val[0]))));
+        if (lc == 0) pb[q][lg][0] = gsum;
+        if (valid) st4(v + s0, val[0], val[1], val[2], val[3]);
+    }
+    __syncthreads();
+    // add the CTA's column blocks (fixed order) and write the partial table of this slot
+    const uint32_t NBr = 1u << KR;
+    double* out = S + sp.stPB + (uint64_t)slot * (KR + 1) * NBr;
+    for (uint32_t t = threadIdx.x; t < G * 8u * (uint32_t)(KR + 1); t += blockDim.x) {
+        const uint32_t e = t % (uint32_t)(KR + 1), rr = (t / (uint32_t)(KR + 1)) & 7u, g = t / ((uint32_t)(KR + 1) * 8u);
+        const uint32_t jB = sg.b + g;
+        const uint32_t ri = jB * 8u + rr;
+        if (jB >= nBg || ri >= nB) continue;
+        double s = 0.0;
+        for (uint32_t ci = 0; ci < C; ++ci) s += pb[g * C + ci][rr][e];
+        out[(uint64_t)e * NBr + hs[offB + ri]] = s;
     }
 }
 
