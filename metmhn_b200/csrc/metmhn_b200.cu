@@ -748,8 +748,8 @@ static int enqueue_eval(mmh_handle* h, const double* d_params, double w0, double
         }
         tick(6);
         if (ck.pf_lo.cnt) {
-            k_pf_lo<<<ck.pf_lo.cnt, 128, 0, st>>>(sp, h->d_items + ck.pf_lo.off, S);
-            k_pf_hi<<<ck.pf_hi.cnt, 128, 0, st>>>(sp, h->d_items + ck.pf_hi.off, S);
+            k_pf_lo<<<ck.pf_lo.cnt, 32 * PF_WARPS, 0, st>>>(sp, h->d_items + ck.pf_lo.off, S);
+            k_pf_hi<<<ck.pf_hi.cnt, 32 * PF_WARPS, 0, st>>>(sp, h->d_items + ck.pf_hi.off, S);
             launches += 2;
         }
         tick(4);

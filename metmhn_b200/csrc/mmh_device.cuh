@@ -1563,7 +1563,7 @@ k_diag_prod(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items,
 // (vanilla.py:328-393 spends n_tot x_partial_Q_y passes on this).  Summing out hi first and lo first gives
 //     H1[r][lo] = sum_hi T2[r][hi] E_r(hi,lo)        H2[r][hi] = sum_lo T1[r][lo] E_r(hi,lo)
 // and k_finish folds T1 H1 over the lo bits, T2 H2 over the hi bits.  A lane owns four consecutive lo (32-byte
-// loads), a warp eight table rows, the four warps of a CTA the 32 rows.
+// loads), a warp PF_RW table rows, the PF_WARPS warps of a CTA the 32 rows.
 // Output (stP): slices x (NR + KA) x N1 partial H1 tables, then (NR + KA) x N2 for H2 (rows >= NR unused).
 __device__ __forceinline__ void pf_E(int kind, int bit, uint32_t hi, uint32_t lo0, int K1, const double* __restrict__ x,
                                      const double (&xv)[4], const double (&yv)[4], const double (&ng)[4], double (&e)[4], bool& zero)
@@ -1595,8 +1595,9 @@ __device__ __forceinline__ void pf_E(int kind, int bit, uint32_t hi, uint32_t lo
     for (int t = 0; t < 4; ++t) e[t] = yv[t] * (xa[t] - xv[t]);
 }
 
+constexpr int PF_RW = 4, PF_WARPS = NR / PF_RW, PF_HB = 4;   // table rows per warp, warps per CTA, hi per k_pf_hi item
 // item: a = block of 128 lo, b = hi slice
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(32 * PF_WARPS, 3)
 k_pf_lo(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, double* __restrict__ S)
 {
     __shared__ PfRows rows;
@@ -1614,12 +1615,12 @@ k_pf_lo(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, dou
     const double* x = S + sp.x_off;
     const double* y = S + sp.y_off;
     const double* T2 = S + sp.tabA + ((uint64_t)NR << K1);
-    int kind[8], bit[8];
+    int kind[PF_RW], bit[PF_RW];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { kind[j] = rows.kind[rg * 8 + j]; bit[j] = rows.bit[rg * 8 + j]; }
-    double acc[8][4];
+    for (int j = 0; j < PF_RW; ++j) { kind[j] = rows.kind[rg * PF_RW + j]; bit[j] = rows.bit[rg * PF_RW + j]; }
+    double acc[PF_RW][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+    for (int j = 0; j < PF_RW; ++j)
 #pragma unroll
         for (int t = 0; t < 4; ++t) acc[j][t] = 0.0;
     for (uint32_t hi = h0; hi < h1; ++hi) {
@@ -1630,29 +1631,28 @@ k_pf_lo(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, dou
 #pragma unroll
         for (int t = 0; t < 4; ++t) ng[t] = -(xv[t] * yv[t]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < PF_RW; ++j) {
             if (kind[j] == 0) continue;
             double e[4];
             bool zero;
             pf_E(kind[j], bit[j], hi, lo0, K1, x, xv, yv, ng, e, zero);
             if (zero) continue;
-            const double tw = T2[((uint64_t)(rg * 8 + j) << K2) + hi];
+            const double tw = T2[((uint64_t)(rg * PF_RW + j) << K2) + hi];
 #pragma unroll
             for (int t = 0; t < 4; ++t) acc[j][t] = fma(tw, e[t], acc[j][t]);
         }
     }
     double* out = S + sp.stP + (uint64_t)it.b * (NR + KA) * N1;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) st4(out + (uint64_t)(rg * 8 + j) * N1 + lo0, acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+    for (int j = 0; j < PF_RW; ++j) st4(out + (uint64_t)(rg * PF_RW + j) * N1 + lo0, acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
 }
 
 // item: a = block of PF_HB hi
-constexpr int PF_HB = 4;
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(32 * PF_WARPS, 2)
 k_pf_hi(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, double* __restrict__ S)
 {
     __shared__ PfRows rows;
-    __shared__ double red[4][8 * PF_HB][33];
+    __shared__ double red[PF_WARPS][PF_RW * PF_HB][33];
     const Item it = items[blockIdx.x];
     const SpaceDev& sp = spaces[it.space];
     pf_rows_build(rows, sp, threadIdx.x);
@@ -1664,12 +1664,12 @@ k_pf_hi(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, dou
     const double* x = S + sp.x_off;
     const double* y = S + sp.y_off;
     const double* T1 = S + sp.tabA;
-    int kind[8], bit[8];
+    int kind[PF_RW], bit[PF_RW];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { kind[j] = rows.kind[rg * 8 + j]; bit[j] = rows.bit[rg * 8 + j]; }
-    double acc[8][PF_HB];
+    for (int j = 0; j < PF_RW; ++j) { kind[j] = rows.kind[rg * PF_RW + j]; bit[j] = rows.bit[rg * PF_RW + j]; }
+    double acc[PF_RW][PF_HB];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+    for (int j = 0; j < PF_RW; ++j)
 #pragma unroll
         for (int h = 0; h < PF_HB; ++h) acc[j][h] = 0.0;
     for (uint32_t lo0 = (uint32_t)lane << 2; lo0 < N1; lo0 += 128) {
@@ -1684,30 +1684,31 @@ k_pf_hi(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, dou
 #pragma unroll
             for (int t = 0; t < 4; ++t) ng[t] = -(xv[t] * yv[t]);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < PF_RW; ++j) {
                 if (kind[j] == 0) continue;
                 double e[4];
                 bool zero;
                 pf_E(kind[j], bit[j], hi, lo0, K1, x, xv, yv, ng, e, zero);
                 if (zero) continue;
                 double tv[4];
-                ld4(T1 + ((uint64_t)(rg * 8 + j) << K1) + lo0, tv);
+                ld4(T1 + ((uint64_t)(rg * PF_RW + j) << K1) + lo0, tv);
                 acc[j][h] = fma(tv[3], e[3], fma(tv[2], e[2], fma(tv[1], e[1], fma(tv[0], e[0], acc[j][h]))));
             }
         }
     }
     // sum over the lanes through shared memory: value q of lane l -> red[q][l]; lane q then adds row q
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+    for (int j = 0; j < PF_RW; ++j)
 #pragma unroll
         for (int h = 0; h < PF_HB; ++h) red[rg][j * PF_HB + h][lane] = acc[j][h];
     __syncwarp();
+    if (lane >= PF_RW * PF_HB) return;
     double s = 0.0;
 #pragma unroll
     for (int l = 0; l < 32; ++l) s += red[rg][lane][l];
     const int j = lane / PF_HB, h = lane % PF_HB;
     double* out = S + sp.stP + (uint64_t)sp.slices * (NR + KA) * N1;
-    if (hb + h < N2) out[(uint64_t)(rg * 8 + j) * N2 + hb + h] = s;
+    if (hb + h < N2) out[(uint64_t)(rg * PF_RW + j) * N2 + hb + h] = s;
 }
 // ------------------------------------------------------------------------------------------
 // Gradient contraction.  For event row i and sub-state u of a group (i not in u)
