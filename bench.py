@@ -248,15 +248,20 @@ def run_ours(args, rank, local_rank, world):
     # algorithmic bytes per class and step: forward writes y (8 B/state), adjoint writes x (8),
     # the contraction reads x and y (16); table setup is pure overhead (0).
     alg = {"setup": 0.0, "solve_fwd": 8.0 * states, "solve_adj": 8.0 * states, "contraction": 16.0 * states}
-    kernels = {"setup": "k_setup, k_setup_wide", "solve_fwd": "k_solve_big4<fwd> (+ k_solve_small*)",
-               "solve_adj": "k_solve_big4<adj> (+ k_solve_small*)",
-               "contraction": "k_stats_a/b, k_pfin_lo/hi, k_finish"}
-    # DRAM traffic of the solve kernel from the committed ncu capture (profiles/r1_v6_solve_big4_ncu_full.txt):
-    # 12.4 bytes per state (read + write) against 8 algorithmic
-    traffic_per_state = {"solve_fwd": 12.4, "solve_adj": 12.4}
+    kernels = {"setup": "k_setup, k_setup_wide, k_diag_prod",
+               "solve_fwd": "k_solve_tile<fwd> (+ k_solve_big4 / k_solve_small* for the generic and small tiers)",
+               "solve_adj": "k_solve_tile_adjb / k_solve_tile<adj> (+ k_solve_big4 / k_solve_small*)",
+               "contraction": "k_stats_a/b, k_pf_lo/hi, k_finish"}
+    # DRAM traffic of the tile solve kernel from the committed ncu capture (profiles/r1_v11_solve_tile_ncu_full.txt):
+    # 22 consecutive level launches of one chunk of 2^23-state pairs, 988 MB read + written for 84.2 M state
+    # updates = 11.7 bytes per state against 8 algorithmic
+    traffic_per_state = {"solve_fwd": 11.7, "solve_adj": 11.7}
+    # the dominant KERNEL is the tile solve (forward and adjoint instantiations); the contraction class is several
+    # kernels, each smaller
+    dominant = "solve_adj" if cls["solve_adj"] >= cls["solve_fwd"] else "solve_fwd"
     if rank == 0:
         fp64_peak = measure_fp64_tflops(local_rank)
-        top = max(alg, key=lambda k: cls[k])
+        top = dominant
         ach = alg[top] / (cls[top] * 1e-3) / 1e9 if cls[top] > 0 else 0.0
         ms_step = 1e3 * wall / args.steps
         # whole-step rooflines use this rank's share of the work and its device time

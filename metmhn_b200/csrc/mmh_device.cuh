@@ -1595,7 +1595,10 @@ __device__ __forceinline__ void pf_E(int kind, int bit, uint32_t hi, uint32_t lo
     for (int t = 0; t < 4; ++t) e[t] = yv[t] * (xa[t] - xv[t]);
 }
 
-constexpr int PF_RW = 4, PF_WARPS = NR / PF_RW, PF_HB = 4;   // table rows per warp, warps per CTA, hi per k_pf_hi item
+#ifndef PF_ROWS_PER_WARP
+#define PF_ROWS_PER_WARP 4
+#endif
+constexpr int PF_RW = PF_ROWS_PER_WARP, PF_WARPS = NR / PF_RW, PF_HB = 4;   // table rows per warp, warps per CTA, hi per k_pf_hi item
 // item: a = block of 128 lo, b = hi slice
 __global__ void __launch_bounds__(32 * PF_WARPS, 3)
 k_pf_lo(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, double* __restrict__ S)

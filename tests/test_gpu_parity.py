@@ -160,3 +160,73 @@ def test_error_paths():
         Handle(bad2)
     h = Handle(np.zeros((0, 9), dtype=np.int8))       # empty dataset is allowed
     assert h.stats()["n_spaces"] == 0
+
+
+def _pair_row(n, pt, mt, order):
+    row = np.zeros(2 * n + 3, dtype=np.int8)
+    for e in pt:
+        row[2 * e] = 1
+    for e in mt:
+        row[2 * e + 1] = 1
+    row[2 * n] = 1
+    row[-2:] = (order, 3)
+    return row
+
+
+def test_tile_kernel_shapes_against_oracle():
+    """Every shape class of the big-tier solve: column blocks below / above 32 per level (fused group-B
+    statistics with several row groups or several column chunks per CTA), few rows, the generic kernel for pairs
+    with fewer than 4 PT bits, shared and private events on both sides."""
+    from metmhn_b200 import Handle
+    from oracle import lattice_direct as ld
+    n = 16
+    rng = np.random.default_rng(1616)
+    th = rng.normal(0.0, 0.4, (n + 1, n + 1))
+    th[np.arange(n + 1), np.arange(n + 1)] = rng.normal(-1.0, 0.5, n + 1)
+    dp, dm = rng.normal(0, 0.3, n + 1), rng.normal(0, 0.3, n + 1)
+    ev = list(range(n))
+    rows = np.stack([
+        _pair_row(n, ev[:12], ev[10:14], 1),          # KA = 12, KB = 4: 70 column blocks at the middle level
+        _pair_row(n, ev[:11], ev[8:13], 0),           # KA = 11, KB = 5, both second phases
+        _pair_row(n, ev[:5], ev[3:13], 2),            # KA = 5,  KB = 10: two column blocks, 16 row groups per CTA
+        _pair_row(n, ev[:3], ev[2:14], 1),            # KA = 3: generic kernel
+        _pair_row(n, ev[:13], ev[13:15], 0),          # KA = 13, KB = 2: few rows, no shared event
+        _pair_row(n, ev[:8], ev[:8], 1),              # identical tumours
+    ])
+    params = np.concatenate([th.ravel(), dp, dm])
+    for r in range(rows.shape[0]):
+        h = Handle(rows[r:r + 1])
+        s, g = h.eval_weighted(params, 1.0, 1.0)
+        s_again, g_again = h.eval_weighted(params, 1.0, 1.0)
+        h.close()
+        assert s == s_again and np.array_equal(g, g_again), r
+        out = ld.patient_value_grad(th, dp, dm, rows[r])
+        assert abs(s - out[1]) <= TOL * abs(out[1]), r
+        assert rel_err(g, np.concatenate([out[2].ravel(), out[3], out[4]])) <= TOL, r
+
+
+def test_alternative_kernel_paths_agree():
+    """The experimental row-block solve (MMH_ROWBLOCK=1) and the unfused statistics path (MMH_FUSE_B=0) give the
+    default path's numbers (the switches are read once per process: run each in a fresh interpreter)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import numpy as np\n"
+            "from metmhn_b200 import Handle\n"
+            "from metmhn_b200.simulate import syn_v1\n"
+            "d = syn_v1(14, 1500, 14014, max_joint_bits=18)\n"
+            "s, g = Handle(d['dat']).value_grad(d['eval_point'], 0.65)\n"
+            "print(repr(float(s))); print(' '.join(repr(float(v)) for v in g))\n") % root
+    res = {}
+    for name, env in (("default", {}), ("rowblock", {"MMH_ROWBLOCK": "1"}), ("unfused", {"MMH_FUSE_B": "0"})):
+        out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr[-2000:]
+        lines = out.stdout.strip().splitlines()
+        res[name] = (float(lines[-2]), np.array([float(v) for v in lines[-1].split()]))
+    s0, g0 = res["default"]
+    for name in ("rowblock", "unfused"):
+        s, g = res[name]
+        assert abs(s - s0) <= 1e-12 * abs(s0), name
+        assert rel_err(g, g0) <= 1e-11, name
