@@ -184,7 +184,19 @@ def run_ours(args, rank, local_rank, world):
 
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL may print its version banner on stdout when the communicator is created; the contract is ONE JSON
+        # line on stdout, so stdout points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     d = workload(args)
     dat, ep = d["dat"], d["eval_point"]
     t0 = time.perf_counter()
@@ -252,10 +264,10 @@ def run_ours(args, rank, local_rank, world):
                "solve_fwd": "k_solve_tile<fwd> (+ k_solve_big4 / k_solve_small* for the generic and small tiers)",
                "solve_adj": "k_solve_tile_adjb / k_solve_tile<adj> (+ k_solve_big4 / k_solve_small*)",
                "contraction": "k_stats_a/b, k_pf_lo/hi, k_finish"}
-    # DRAM traffic of the tile solve kernel from the committed ncu capture (profiles/r1_v11_solve_tile_ncu_full.txt):
-    # 22 consecutive level launches of one chunk of 2^23-state pairs, 988 MB read + written for 84.2 M state
-    # updates = 11.7 bytes per state against 8 algorithmic
-    traffic_per_state = {"solve_fwd": 11.7, "solve_adj": 11.7}
+    # DRAM traffic of the tile solve kernels from the committed ncu capture (profiles/r1_final_solve_tile_ncu_full.txt,
+    # 24 consecutive level launches of one chunk of 2^22..2^23-state pairs): forward 12.9 bytes per state (read +
+    # write) against 8 algorithmic; adjoint with fused group-B statistics 16.9 (it also reads y)
+    traffic_per_state = {"solve_fwd": 12.9, "solve_adj": 16.9}
     # the dominant KERNEL is the tile solve (forward and adjoint instantiations); the contraction class is several
     # kernels, each smaller
     dominant = "solve_adj" if cls["solve_adj"] >= cls["solve_fwd"] else "solve_fwd"
