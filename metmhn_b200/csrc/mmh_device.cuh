@@ -1352,17 +1352,45 @@ k_stats_a(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, u
     const bool valid = uA < NA;
     double g0 = 0.0, g1 = 0.0, a0 = 0.0;             // bit 0: only the even state lacks it
     double l0[5] = {0, 0, 0, 0, 0}, l1[5] = {0, 0, 0, 0, 0};
-    for (uint32_t uB = b0; uB < b1; ++uB) {
-        const uint64_t s = ((uint64_t)uB << KA) | uA;
-        double2 yv = make_double2(0.0, 0.0), xv = yv;
-        if (valid) { yv = *reinterpret_cast<const double2*>(y + s); xv = *reinterpret_cast<const double2*>(x + s); }
-        g0 = fma(xv.x, yv.x, g0); g1 = fma(xv.y, yv.y, g1);
-        a0 = fma(yv.x, xv.y, a0);
+    // Bits 6..15 are uniform over the warp's 64 sub-states.  The slab of rows is walked in sub-slabs of SUB rows: bits
+    // 0..5 first, then one short loop per absent high bit over the SAME rows, whose y values are still in L1 (walking
+    // the whole slab once per high bit re-read it from DRAM 3x, profiles/r1_v11 capture).
+    constexpr int HB0 = 6, MAXHB = 10, SUB = 16;
+    double h0[MAXHB], h1[MAXHB];
 #pragma unroll
-        for (int a = 1; a <= 5; ++a) {
-            const double px = __shfl_xor_sync(0xffffffffu, xv.x, 1 << (a - 1));
-            const double py = __shfl_xor_sync(0xffffffffu, xv.y, 1 << (a - 1));
-            if (a < KA && !((lane >> (a - 1)) & 1)) { l0[a - 1] = fma(yv.x, px, l0[a - 1]); l1[a - 1] = fma(yv.y, py, l1[a - 1]); }
+    for (int q = 0; q < MAXHB; ++q) { h0[q] = 0.0; h1[q] = 0.0; }
+    uint32_t hmask = 0;
+    if (valid)
+        for (int a = HB0; a < KA && a < HB0 + MAXHB; ++a) if (!((uA >> a) & 1u)) hmask |= 1u << (a - HB0);
+    for (uint32_t u0 = b0; u0 < b1; u0 += SUB) {
+        const uint32_t u1 = min(b1, u0 + SUB);
+#pragma unroll 4
+        for (uint32_t uB = u0; uB < u1; ++uB) {
+            const uint64_t s = ((uint64_t)uB << KA) | uA;
+            double2 yv = make_double2(0.0, 0.0), xv = yv;
+            if (valid) { yv = *reinterpret_cast<const double2*>(y + s); xv = *reinterpret_cast<const double2*>(x + s); }
+            g0 = fma(xv.x, yv.x, g0); g1 = fma(xv.y, yv.y, g1);
+            a0 = fma(yv.x, xv.y, a0);
+#pragma unroll
+            for (int a = 1; a <= 5; ++a) {
+                const double px = __shfl_xor_sync(0xffffffffu, xv.x, 1 << (a - 1));
+                const double py = __shfl_xor_sync(0xffffffffu, xv.y, 1 << (a - 1));
+                if (a < KA && !((lane >> (a - 1)) & 1)) { l0[a - 1] = fma(yv.x, px, l0[a - 1]); l1[a - 1] = fma(yv.y, py, l1[a - 1]); }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < MAXHB; ++q) {
+            if (!((hmask >> q) & 1u)) continue;
+            const uint64_t bit = (uint64_t)64 << q;
+            double e0 = 0.0, e1 = 0.0;
+#pragma unroll 4
+            for (uint32_t uB = u0; uB < u1; ++uB) {
+                const uint64_t s = ((uint64_t)uB << KA) | uA;
+                const double2 yv = *reinterpret_cast<const double2*>(y + s);
+                const double2 xa = *reinterpret_cast<const double2*>(x + (s | bit));
+                e0 = fma(yv.x, xa.x, e0); e1 = fma(yv.y, xa.y, e1);
+            }
+            h0[q] += e0; h1[q] += e1;
         }
     }
     if (valid) {
@@ -1371,21 +1399,24 @@ k_stats_a(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, u
 #pragma unroll
         for (int a = 1; a <= 5; ++a)
             if (a < KA) { out[(uint64_t)(1 + a) * NA + uA] = l0[a - 1]; out[(uint64_t)(1 + a) * NA + uA + 1] = l1[a - 1]; }
+#pragma unroll
+        for (int q = 0; q < MAXHB; ++q)
+            if (HB0 + q < KA) { out[(uint64_t)(1 + HB0 + q) * NA + uA] = h0[q]; out[(uint64_t)(1 + HB0 + q) * NA + uA + 1] = h1[q]; }
     }
-    // bits >= 6: uniform over the chunk; y is re-read from L1
-    for (int a = 6; a < KA; ++a) {
+    // bits >= 16 (wide group): one sweep of the slab per bit
+    for (int a = HB0 + MAXHB; a < KA; ++a) {
         if (!valid) break;
-        double h0 = 0.0, h1 = 0.0;
+        double e0 = 0.0, e1 = 0.0;
         if (!((uA >> a) & 1u)) {
             const uint64_t bit = 1ull << a;
             for (uint32_t uB = b0; uB < b1; ++uB) {
                 const uint64_t s = ((uint64_t)uB << KA) | uA;
                 const double2 yv = *reinterpret_cast<const double2*>(y + s);
                 const double2 xa = *reinterpret_cast<const double2*>(x + (s | bit));
-                h0 = fma(yv.x, xa.x, h0); h1 = fma(yv.y, xa.y, h1);
+                e0 = fma(yv.x, xa.x, e0); e1 = fma(yv.y, xa.y, e1);
             }
         }
-        out[(uint64_t)(1 + a) * NA + uA] = h0; out[(uint64_t)(1 + a) * NA + uA + 1] = h1;
+        out[(uint64_t)(1 + a) * NA + uA] = e0; out[(uint64_t)(1 + a) * NA + uA + 1] = e1;
     }
 }
 
