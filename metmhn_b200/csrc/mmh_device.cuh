@@ -1352,10 +1352,16 @@ k_stats_a(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, u
     const bool valid = uA < NA;
     double g0 = 0.0, g1 = 0.0, a0 = 0.0;             // bit 0: only the even state lacks it
     double l0[5] = {0, 0, 0, 0, 0}, l1[5] = {0, 0, 0, 0, 0};
-    // Bits 6..15 are uniform over the warp's 64 sub-states.  The slab of rows is walked in sub-slabs of SUB rows: bits
+    // Bits 6..11 are uniform over the warp's 64 sub-states.  The slab of rows is walked in sub-slabs of SUB rows: bits
     // 0..5 first, then one short loop per absent high bit over the SAME rows, whose y values are still in L1 (walking
     // the whole slab once per high bit re-read it from DRAM 3x, profiles/r1_v11 capture).
-    constexpr int HB0 = 6, MAXHB = 10, SUB = 16;
+#ifndef STA_MAXHB
+#define STA_MAXHB 6             // column bits 6..11 with register accumulators (A/B tested against 10)
+#endif
+#ifndef STA_SUB
+#define STA_SUB 16
+#endif
+    constexpr int HB0 = 6, MAXHB = STA_MAXHB, SUB = STA_SUB;
     double h0[MAXHB], h1[MAXHB];
 #pragma unroll
     for (int q = 0; q < MAXHB; ++q) { h0[q] = 0.0; h1[q] = 0.0; }
@@ -1403,7 +1409,7 @@ k_stats_a(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, u
         for (int q = 0; q < MAXHB; ++q)
             if (HB0 + q < KA) { out[(uint64_t)(1 + HB0 + q) * NA + uA] = h0[q]; out[(uint64_t)(1 + HB0 + q) * NA + uA + 1] = h1[q]; }
     }
-    // bits >= 16 (wide group): one sweep of the slab per bit
+    // bits >= 6 + MAXHB: one sweep of the slab per bit
     for (int a = HB0 + MAXHB; a < KA; ++a) {
         if (!valid) break;
         double e0 = 0.0, e1 = 0.0;
