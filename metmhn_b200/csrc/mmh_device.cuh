@@ -468,23 +468,6 @@ k_solve_small(const SpaceDev* __restrict__ spaces, const uint32_t* __restrict__ 
     }
 }
 
-// big tier: one launch per popcount level of the block index; a segment is up to SEGB blocks of one
-// space at that level (popcount-sorted block index table `hs`).
-template <bool ADJ>
-__global__ void __launch_bounds__(256)
-k_solve_big(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs,
-            const uint32_t* __restrict__ hs, double* __restrict__ S)
-{
-    __shared__ SpaceCtx ctx;
-    const Item sg = segs[blockIdx.x];
-    const SpaceDev& sp = spaces[sg.space];
-    ctx_build(ctx, sp, S, threadIdx.x);
-    __syncthreads();
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (uint32_t r = w; r < sg.b; r += nw)
-        solve_block<ADJ>(sp, spaces, ctx, S, hs[sg.a + r], lane);
-}
-
 // ------------------------------------------------------------------------------------------
 // Four states per lane.  A warp owns 128 consecutive states: bits 0,1 live inside the lane (registers),
 // bits 2..6 across the lanes, bits >= 7 select the block.  The index arithmetic of an edge bit is done once
