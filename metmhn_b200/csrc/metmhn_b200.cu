@@ -70,8 +70,8 @@ struct mmh_handle {
     // buffer and gradient partials: the thin popcount levels and the tails of one chunk overlap with the work
     // of the others.  Chunk -> stream is static and k_final adds the slots in a fixed order: results stay
     // bit-identical from call to call.
-    static constexpr int NS = 32;                // most side streams; `ns` of them are used (MMH_STREAMS, default 12)
-    int ns = 12;
+    static constexpr int NS = 32;                // most side streams; `ns` of them are used (MMH_STREAMS, default 6)
+    int ns = 6;
     cudaStream_t stream = nullptr;               // main stream: parameters, k_prep, k_final, copies
     cudaStream_t side[NS] = {};
     cudaEvent_t ev_side[NS] = {}, ev_prep = nullptr;
