@@ -1696,6 +1696,15 @@ k_pf_hi(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, dou
 #pragma unroll
         for (int h = 0; h < PF_HB; ++h) acc[j][h] = 0.0;
     for (uint32_t lo0 = (uint32_t)lane << 2; lo0 < N1; lo0 += 128) {
+        double tvr[PF_RW][4];                            // T1 rows of this warp at the lane's columns: shared by the PF_HB hi
+#pragma unroll
+        for (int j = 0; j < PF_RW; ++j) {
+            if (kind[j] != 0) ld4(T1 + ((uint64_t)(rg * PF_RW + j) << K1) + lo0, tvr[j]);
+            else {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) tvr[j][t] = 0.0;
+            }
+        }
 #pragma unroll
         for (int h = 0; h < PF_HB; ++h) {
             const uint32_t hi = hb + h;
@@ -1713,9 +1722,7 @@ k_pf_hi(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, dou
                 bool zero;
                 pf_E(kind[j], bit[j], hi, lo0, K1, x, xv, yv, ng, e, zero);
                 if (zero) continue;
-                double tv[4];
-                ld4(T1 + ((uint64_t)(rg * PF_RW + j) << K1) + lo0, tv);
-                acc[j][h] = fma(tv[3], e[3], fma(tv[2], e[2], fma(tv[1], e[1], fma(tv[0], e[0], acc[j][h]))));
+                acc[j][h] = fma(tvr[j][3], e[3], fma(tvr[j][2], e[2], fma(tvr[j][1], e[1], fma(tvr[j][0], e[0], acc[j][h]))));
             }
         }
     }
