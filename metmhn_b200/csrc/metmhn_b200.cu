@@ -573,7 +573,7 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
     // ---- upload -----------------------------------------------------------------------------------------
     cudaDeviceProp prop{};
     CK(cudaGetDeviceProperties(&prop, device));
-    h->fin_ctas = prop.multiProcessorCount * 2;
+    h->fin_ctas = prop.multiProcessorCount * 3;          // three k_finish CTAs fit one SM (58 KB of shared memory each)
     auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
         cudaError_t e = cudaMalloc(dst, std::max<size_t>(bytes, 16));
         if (e != cudaSuccess) return e;
