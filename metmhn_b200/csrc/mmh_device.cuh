@@ -695,7 +695,10 @@ k_solve_big4(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs,
 // the column-rate loads of the 8 row groups hit the same line.  One launch per level lA + lB.
 constexpr int TILES_PER_CTA = 32;
 #ifndef TILE_CTAS
-#define TILE_CTAS 3
+#define TILE_CTAS 4            // resident CTAs per SM of k_solve_tile (64 registers; 3 measured 1.2 % slower)
+#endif
+#ifndef ADJB_CTAS
+#define ADJB_CTAS 3
 #endif
 #ifndef TILE_NBA
 #define TILE_NBA 2            // column-bit edges in flight per round
@@ -1009,7 +1012,7 @@ __device__ __forceinline__ double group4_sum(double v)
     return v;
 }
 
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, ADJB_CTAS)
 k_solve_tile_adjb(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs, const uint32_t* __restrict__ hs,
                   const uint32_t* __restrict__ hsidx, double* __restrict__ S)
 {
