@@ -61,6 +61,10 @@ struct mmh_handle {
     Item* d_items = nullptr;
     uint32_t* d_hs = nullptr;
     uint32_t* d_hsidx = nullptr;                 // [bits][level] -> first entry of that popcount level in d_hs
+    uint32_t* d_ctr = nullptr;                   // MMH_SMLOCAL=1: per-launch, per-SM work queue counters
+    uint32_t ctr_launches = 0;                   // fat tile launches per evaluation (capacity of d_ctr)
+    int nsm = 0, smlocal = 0;
+    uint32_t smlocal_min = 0;                    // launches with more items than this use the SM-local kernel
     uint8_t* d_cls = nullptr;
     double* d_cnt = nullptr;
     EvalPar* d_par = nullptr;
@@ -573,6 +577,16 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
     // ---- upload -----------------------------------------------------------------------------------------
     cudaDeviceProp prop{};
     CK(cudaGetDeviceProperties(&prop, device));
+    h->nsm = prop.multiProcessorCount;
+    if (const char* e = std::getenv("MMH_SMLOCAL")) h->smlocal = std::atoi(e) != 0;
+    h->smlocal_min = (uint32_t)(TILE_CTAS * h->nsm);
+    if (const char* e = std::getenv("MMH_SMLOCAL_MIN")) h->smlocal_min = (uint32_t)std::max(0, std::atoi(e));
+    if (h->smlocal) {
+        for (const ChunkPlan& ck : h->chunks)
+            for (const std::vector<Range>* lv : {&ck.main_lvt, &ck.sec_lvt, &ck.sec_lvt, &ck.main_lvt_adj})     // sec: both passes
+                for (const Range& r : *lv) if (r.cnt > h->smlocal_min) ++h->ctr_launches;
+        CK(cudaMalloc((void**)&h->d_ctr, std::max<size_t>(1, (size_t)h->ctr_launches * h->nsm) * sizeof(uint32_t)));
+    }
     h->fin_ctas = prop.multiProcessorCount * 3;          // three k_finish CTAs fit one SM (58 KB of shared memory each)
     auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
         cudaError_t e = cudaMalloc(dst, std::max<size_t>(bytes, 16));
@@ -642,6 +656,8 @@ static int enqueue_eval(mmh_handle* h, const double* d_params, double w0, double
     };
     tick(5);
     k_prep<<<1, 1024, 0, st>>>(d_params, h->n_tot, h->d_par); ++launches;
+    if (h->smlocal && h->ctr_launches) CK(cudaMemsetAsync(h->d_ctr, 0, (size_t)h->ctr_launches * h->nsm * sizeof(uint32_t), st));
+    uint32_t ctr_idx = 0;
     if (want_grad) {
         CK(cudaMemsetAsync(h->d_partial, 0, (size_t)NS * h->fin_ctas * NACC * NR * NR * sizeof(double), st));
         CK(cudaMemsetAsync(h->d_diracc, 0, (size_t)NS * 2 * NR * sizeof(double), st));
@@ -692,7 +708,12 @@ static int enqueue_eval(mmh_handle* h, const double* d_params, double w0, double
             for (int q = 0; q < L; ++q) {
                 const Range& r = lv[adj ? L - 1 - q : q];
                 if (!r.cnt) continue;
-                if (adj) k_solve_tile<true><<<r.cnt, 256, 0, st>>>(sp, h->d_items + r.off, h->d_hs, h->d_hsidx, S);
+                if (h->smlocal && r.cnt > h->smlocal_min && ctr_idx < h->ctr_launches) {
+                    uint32_t* ctr = h->d_ctr + (size_t)ctr_idx++ * h->nsm;
+                    const uint32_t grid = std::min<uint32_t>(r.cnt, (uint32_t)(TILE_CTAS * h->nsm));
+                    if (adj) k_solve_tile_sm<true><<<grid, 256, 0, st>>>(sp, h->d_items + r.off, r.cnt, h->d_hs, h->d_hsidx, S, ctr, (uint32_t)h->nsm);
+                    else     k_solve_tile_sm<false><<<grid, 256, 0, st>>>(sp, h->d_items + r.off, r.cnt, h->d_hs, h->d_hsidx, S, ctr, (uint32_t)h->nsm);
+                } else if (adj) k_solve_tile<true><<<r.cnt, 256, 0, st>>>(sp, h->d_items + r.off, h->d_hs, h->d_hsidx, S);
                 else     k_solve_tile<false><<<r.cnt, 256, 0, st>>>(sp, h->d_items + r.off, h->d_hs, h->d_hsidx, S);
                 ++launches;
             }
@@ -927,7 +948,7 @@ extern "C" void mmh_destroy(mmh_handle* h)
 {
     if (!h) return;
     cudaSetDevice(h->device);
-    cudaFree(h->d_spaces); cudaFree(h->d_lists); cudaFree(h->d_items); cudaFree(h->d_hs); cudaFree(h->d_hsidx); cudaFree(h->d_cls);
+    cudaFree(h->d_spaces); cudaFree(h->d_lists); cudaFree(h->d_items); cudaFree(h->d_hs); cudaFree(h->d_hsidx); cudaFree(h->d_ctr); cudaFree(h->d_cls);
     cudaFree(h->d_cnt); cudaFree(h->d_par); cudaFree(h->d_params); cudaFree(h->d_logp);
     for (int q = 0; q < mmh_handle::NS; ++q) {
         cudaFree(h->d_scratch_s[q]);

@@ -994,6 +994,89 @@ k_solve_tile(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs,
     }
 }
 
+// Experimental SM-local scheduling of the tile solve (MMH_SMLOCAL=1, fat levels only).  Every source line of a
+// row edge is read by the ~KR/2 successor rows of the same column block; launched as independent CTAs those readers
+// are scattered over the SMs and every read goes to L2 (76 B of L2 traffic per state).  Here the items of a launch
+// are split into windows of SM_WIN consecutive items (about one column block with all its rows of the level);
+// window j belongs to the queue of SM j % nsm, a persistent CTA pulls items from the queue of the SM it runs on
+// (%smid), so that the readers of a line share one L1.  When its queue is empty a CTA helps with whatever queue still
+// has items (needed for correctness too: an SM may host no CTA of this launch).  Results do not depend on which CTA
+// runs an item.
+constexpr uint32_t SM_WIN = 4;
+
+__device__ __forceinline__ uint32_t smq_len(uint32_t q, uint32_t n_items, uint32_t nsm)
+{
+    // items of queue q: windows q, q + nsm, ... each SM_WIN items, the last one possibly cut by n_items
+    const uint32_t nwin = (n_items + SM_WIN - 1) / SM_WIN;
+    if (q >= nwin) return 0;
+    const uint32_t mine = (nwin - 1 - q) / nsm + 1;              // windows of this queue
+    const uint32_t last = q + (mine - 1) * nsm;                  // its last window
+    const uint32_t in_last = min(SM_WIN, n_items - last * SM_WIN);
+    return (mine - 1) * SM_WIN + in_last;
+}
+
+template <bool ADJ>
+__global__ void __launch_bounds__(256, TILE_CTAS)
+k_solve_tile_sm(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs, uint32_t n_items,
+                const uint32_t* __restrict__ hs, const uint32_t* __restrict__ hsidx, double* __restrict__ S,
+                uint32_t* __restrict__ ctr, uint32_t nsm)
+{
+    __shared__ TileCtx ctx;
+    __shared__ uint32_t s_item, s_queue;
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t queue = smid % nsm, cur_space = 0xffffffffu;
+    for (;;) {
+        // ---- next item of the current queue ----
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t id = 0xffffffffu;
+            if (queue != 0xffffffffu) {
+                const uint32_t k = atomicAdd(&ctr[queue], 1u);
+                if (k < smq_len(queue, n_items, nsm)) id = (queue + nsm * (k / SM_WIN)) * SM_WIN + (k % SM_WIN);
+            }
+            s_item = id;
+        }
+        __syncthreads();
+        uint32_t id = s_item;
+        if (id == 0xffffffffu) {
+            // ---- queue empty: look for any queue that still has items ----
+            if (threadIdx.x == 0) s_queue = 0xffffffffu;
+            __syncthreads();
+            for (uint32_t q = threadIdx.x; q < nsm; q += blockDim.x)
+                if (*reinterpret_cast<volatile uint32_t*>(ctr + q) < smq_len(q, n_items, nsm)) atomicMin(&s_queue, q);
+            __syncthreads();
+            queue = s_queue;
+            if (queue == 0xffffffffu) return;                    // every queue is drained (uniform over the CTA)
+            continue;
+        }
+        const Item sg = segs[id];
+        const SpaceDev& sp = spaces[sg.space];
+        if (sg.space != cur_space) {
+            tile_ctx_build(ctx, sp, S, threadIdx.x);
+            cur_space = sg.space;
+            __syncthreads();
+        }
+        const uint32_t lA = sg.a & 255u, lB = (sg.a >> 8) & 255u, cnt = sg.a >> 16;
+        const uint32_t offA = hsidx[(ctx.KC - 4) * 32 + lA];
+        const uint32_t offB = hsidx[ctx.KR * 32 + lB];
+        const uint32_t nB = hsidx[ctx.KR * 32 + lB + 1] - offB;
+        const uint32_t nBg = (nB + 7u) >> 3;
+        const bool prod = sp.kind != K_JOINT;
+        for (uint32_t q = w; q < cnt; q += 8) {
+            const uint32_t t = sg.b + q;
+            const uint32_t iA = t / nBg, jB = t - iA * nBg;
+            const uint32_t ri = jB * 8u + (uint32_t)(lane >> 2);
+            const bool valid = ri < nB;
+            const uint32_t cA = hs[offA + iA];
+            const uint32_t row = hs[offB + min(ri, nB - 1u)];
+            if (prod) solve_tile16<ADJ, true>(sp, spaces, ctx, S, cA, row, valid, lane);
+            else      solve_tile16<ADJ, false>(sp, spaces, ctx, S, cA, row, valid, lane);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Adjoint tile solve of a pair with the group-B marginal statistics fused in.  The adjoint pass already holds, for
 // every state s and every row bit b not in s, the value x[s + b]; with y[s] (one more 32-byte load) the lane adds
