@@ -303,7 +303,13 @@ def run_ours(args, rank, local_rank, world):
                          "algorithmic_GB_per_step": alg[top] / 1e9, "class_ms_serial": cls[top],
                          "peak_source": peak_src,
                          "note": "class time = CUDA events on the launching stream in the library's profile mode "
-                                 "(chunks serialised on one stream); the timed steps overlap chunks on side streams"},
+                                 "(chunks serialised on one stream); the timed steps overlap chunks on side streams",
+                         "binding_resource": {
+                             "what": "random 128-byte line reads through L2 (every state reads ~K/2 finished neighbours)",
+                             "kernel_L2_sector_traffic_TBs": [6.0, 6.4], "kernel_L2_hit_rate": 0.6,
+                             "ceiling_TBs": {"lines_in_L2_24_warps_per_SM": 6.7, "lines_in_HBM_24_warps_per_SM": 4.0},
+                             "source": "profiles/r1_final_solve_tile_ncu_full.txt, profiles/r1_microbench_line_reads.txt "
+                                       "(scripts/microbench/line_reads.cu); measured once per round, not in this run"}},
             "roofline_step": {"hbm": {"achieved_GBs": st["alg_bytes"] / t_rank / 1e9, "peak_GBs": peaks["hbm_gbs"], "frac": hbm_frac},
                               "fp64": {"achieved_TFLOPs": st["alg_flops"] / t_rank / 1e12, "peak_TFLOPs": fp64_peak,
                                        "frac": fp_frac, "peak_source": "independent-DFMA micro-kernel, this run"},
