@@ -42,6 +42,7 @@ struct ChunkPlan {
     std::vector<Range> main_lvt, sec_lvt;        // big-tier tiles per level (tiled kernel)
     std::vector<Range> main_lvr, sec_lvr;        // big-tier row blocks per row level (row-block kernel)
     std::vector<Range> main_lvt_adj, main_lvt_adjb;  // adjoint pass of the main tiled spaces: plain / with fused B statistics
+    std::vector<Range> main_lvb;                 // forward pass of pairs with the two-dimensional blocked kernel (MMH_BLOCK=1)
     uint64_t scratch = 0;                        // doubles
 };
 
@@ -64,6 +65,7 @@ struct mmh_handle {
     uint32_t* d_ctr = nullptr;                   // MMH_SMLOCAL=1: per-launch, per-SM work queue counters
     uint32_t ctr_launches = 0;                   // fat tile launches per evaluation (capacity of d_ctr)
     int nsm = 0, smlocal = 0;
+    int block_version = 0;                       // MMH_BLOCK: 1 = blocked forward solve (tested), 2 = with staged rates (untested)
     uint32_t smlocal_min = 0;                    // launches with more items than this use the SM-local kernel
     uint8_t* d_cls = nullptr;
     double* d_cnt = nullptr;
@@ -511,9 +513,45 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
                 lv[l].cnt = (uint32_t)(items.size() - lv[l].off);
             }
         };
+        // experimental two-dimensional blocked forward solve (k_solve_block_fwd): pairs only, MMH_BLOCK=1
+        static const int block_version = [] { const char* e = std::getenv("MMH_BLOCK"); return e ? std::atoi(e) : 0; }();
+        static const bool use_block = block_version != 0;
+        auto blocked = [&](const SpaceDev& s) {
+            if (!use_block || !fused_b(s) || rowblock(s)) return false;
+            int d_c, d_r;
+            block_dims(s.KA, s.KB, d_c, d_r);
+            if (block_version == 2 && d_c > 4) return false;        // version 2 stages at most 8 rate rows of 256 columns
+            return d_c + d_r >= 4;
+        };
+        auto levels_of_b = [&](std::vector<Range>& lv) {
+            int maxl = -1;
+            for (uint32_t i = 0; i < ck.nspaces; ++i)
+                if (blocked(sp[i])) { int d_c, d_r; block_dims(sp[i].KA, sp[i].KB, d_c, d_r); maxl = std::max(maxl, (int)sp[i].KA - 4 - d_c + (int)sp[i].KB - d_r); }
+            if (maxl < 0) return;
+            lv.resize(maxl + 1);
+            for (int l = 0; l <= maxl; ++l) {
+                lv[l].off = items.size();
+                for (uint32_t i = 0; i < ck.nspaces; ++i) {
+                    if (!blocked(sp[i])) continue;
+                    int d_c, d_r;
+                    block_dims(sp[i].KA, sp[i].KB, d_c, d_r);
+                    const int kbA = sp[i].KA - 4 - d_c, kbB = sp[i].KB - d_r;
+                    if (l > kbA + kbB) continue;
+                    need_hs(kbA); need_hs(kbB); need_hs(d_c + d_r);
+                    for (int lA = std::max(0, l - kbB); lA <= std::min(kbA, l); ++lA) {
+                        const int lB = l - lA;
+                        const uint64_t nA = hs_lvl[kbA][lA + 1] - hs_lvl[kbA][lA];
+                        const uint64_t nB = hs_lvl[kbB][lB + 1] - hs_lvl[kbB][lB];
+                        for (uint64_t t = 0; t < nA * nB; ++t) items.push_back({i, (uint32_t)lA | ((uint32_t)lB << 8), (uint32_t)t});
+                    }
+                }
+                lv[l].cnt = (uint32_t)(items.size() - lv[l].off);
+            }
+        };
         levels_of(is_main, ck.main_lv);
         levels_of(is_sec, ck.sec_lv);
-        levels_of_t(is_main, ck.main_lvt);
+        levels_of_t([&](const SpaceDev& s) { return is_main(s) && !blocked(s); }, ck.main_lvt);
+        levels_of_b(ck.main_lvb);
         levels_of_t([&](const SpaceDev& s) { return is_main(s) && !fused_b(s); }, ck.main_lvt_adj);
         levels_of_adjb(ck.main_lvt_adjb);
         levels_of_t(is_sec, ck.sec_lvt);
@@ -629,6 +667,8 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
+    if (const char* e = std::getenv("MMH_BLOCK")) h->block_version = std::atoi(e);
+    CK(cudaFuncSetAttribute(k_solve_block_fwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BLK2_SMEM_DOUBLES * sizeof(double))));
     CK(cudaFuncSetAttribute(k_solve_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
     CK(cudaFuncSetAttribute(k_solve_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
     CK(cudaFuncSetAttribute(k_finish<MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIN_SMEM));
@@ -736,6 +776,14 @@ static int enqueue_eval(mmh_handle* h, const double* d_params, double w0, double
         small(ck.pre, false); small4(ck.pre4, false);
         small(ck.main_small, false); small4(ck.main_small4, false);
         big(ck.main_lv, false); bigt(ck.main_lvt, false); bigr(ck.main_lvr, false);
+        for (const Range& r : ck.main_lvb) {
+            if (!r.cnt) continue;
+            if (h->block_version == 2)
+                k_solve_block_fwd2<<<r.cnt, 256, BLK2_SMEM_DOUBLES * sizeof(double), st>>>(sp, h->d_items + r.off, h->d_hs, h->d_hsidx, S);
+            else
+                k_solve_block_fwd<<<r.cnt, 256, BLK_STATES * sizeof(double), st>>>(sp, h->d_items + r.off, h->d_hs, h->d_hsidx, S);
+            ++launches;
+        }
         small(ck.sec_small, false); small4(ck.sec_small4, false);
         big(ck.sec_lv, false); bigt(ck.sec_lvt, false); bigr(ck.sec_lvr, false);
         tick(5);

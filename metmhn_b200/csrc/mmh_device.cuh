@@ -1078,6 +1078,370 @@ k_solve_tile_sm(const SpaceDev* __restrict__ spaces, const Item* __restrict__ se
 }
 
 // ------------------------------------------------------------------------------------------
+// Two-dimensional blocked forward solve of a pair (experimental, MMH_BLOCK=1).  A CTA owns the
+// sub-lattice spanned by the d_r LOWEST row bits and the d_c LOWEST column-block bits (plus the 4 in-tile column
+// bits): 2^(d_r + d_c + 4) <= BLK_STATES states held in shared memory, i.e. rows rH 2^d_r + rl (rl < 2^d_r) and the
+// 2^(d_c + 4) consecutive columns of column blocks cH 2^d_c + cl.  Launch levels run over popcount(cH) + popcount(rH)
+// only.  Phase 1 adds, for every 16-state tile (rl, cl) of the block, the right-hand side and the edges on the bits of
+// cH and rH (sources are blocks finished by earlier launches; uniform trip counts over the whole CTA).  Phase 2 walks the
+// d + 1 inner levels of the combined index m = rl << d_c | cl (popcount-sorted list of d-bit numbers) with
+// __syncthreads in between: edges on inside bits read shared memory, bits 0..3 are resolved by tile_tail.  The 128-byte
+// line reads per state drop from (K - 4) / 2 to (K - 4 - d) / 2.
+constexpr int BLK_STATES = 4096;
+constexpr int BLK_D = 8;                             // inside bits (rows + column blocks)
+
+__host__ __device__ inline void block_dims(int KA, int KB, int& d_c, int& d_r)
+{
+    d_c = KA - 4 < 4 ? KA - 4 : 4;
+    d_r = KB < BLK_D - d_c ? KB : BLK_D - d_c;
+    if (d_c + d_r < BLK_D) d_c = KA - 4 < BLK_D - d_r ? KA - 4 : BLK_D - d_r;
+}
+
+// item: a = lA' | lB' << 8 (popcounts of the outside column-block / row bits), b = block index inside the split
+__global__ void __launch_bounds__(256, 3)
+k_solve_block_fwd(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs, const uint32_t* __restrict__ hs,
+                  const uint32_t* __restrict__ hsidx, double* __restrict__ S)
+{
+    extern __shared__ double Yt[];                    // [rl][cl * 16 + column], row stride 2^(d_c + 4)
+    __shared__ TileCtx ctx;
+    const Item sg = segs[blockIdx.x];
+    const SpaceDev& sp = spaces[sg.space];
+    tile_ctx_build(ctx, sp, S, threadIdx.x);
+    __syncthreads();
+    const TileCtx& c = ctx;
+    const int KC = c.KC, KR = c.KR;
+    int d_c, d_r;
+    block_dims(KC, KR, d_c, d_r);
+    const int d = d_c + d_r, kbA = KC - 4 - d_c, kbB = KR - d_r;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, lc = lane & 3, lg = lane >> 2;
+    const uint32_t lA = sg.a & 255u, lB = (sg.a >> 8) & 255u;
+    const uint32_t offA = hsidx[kbA * 32 + lA];
+    const uint32_t offB = hsidx[kbB * 32 + lB], nBo = hsidx[kbB * 32 + lB + 1] - offB;
+    const uint32_t iA = sg.b / nBo, iB = sg.b - iA * nBo;
+    const uint32_t cH = hs[offA + iA], rH = hs[offB + iB];
+    const uint32_t rs = 1u << (d_c + 4);              // row stride of the shared block
+    const uint32_t ntile = 1u << d;
+    double* v = S + sp.y_off;
+    // ---- phase 1: right-hand side and edges on the outside bits, tiles in natural order ----
+    for (uint32_t m0 = (uint32_t)w * 8u; m0 < ntile; m0 += 64u) {
+        const uint32_t m = min(m0 + (uint32_t)lg, ntile - 1u);
+        const bool valid = m0 + (uint32_t)lg < ntile;
+        const uint32_t rl = m >> d_c, cl = m & ((1u << d_c) - 1u);
+        const uint32_t row = (rH << d_r) | rl;
+        const uint32_t cA = (cH << d_c) | cl;
+        const uint32_t lo0 = (cA << 4) | ((uint32_t)lc << 2);
+        const uint32_t s0 = (row << KC) | lo0;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        tile_rhs<false>(sp, spaces, S, KC, KR, row, lo0, acc);
+        {
+            constexpr int NB = TILE_NBA;
+            uint32_t mm = cH;                            // outside column-block bits: uniform over the CTA
+            while (mm) {
+                double r[NB][4], y[NB][4];
+#pragma unroll
+                for (int e = 0; e < NB; ++e) {
+                    const bool on = mm != 0u;
+                    const int a = on ? __ffs(mm) + 3 + d_c : 4;
+                    mm &= mm - 1;
+                    const uint32_t bit = 1u << a;
+                    if (on) { ld4(c.colA[a] + (lo0 ^ bit), r[e]); ld4(v + (s0 ^ bit), y[e]); }
+                    else {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) { r[e][t] = 0.0; y[e][t] = 0.0; }
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < NB; ++e)
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) acc[t] = fma(r[e][t], y[e][t], acc[t]);
+            }
+        }
+        {
+            constexpr int NB = TILE_NBB;
+            uint32_t mm = rH;                            // outside row bits: uniform over the CTA
+            while (mm) {
+                double y[NB][4], k[NB];
+#pragma unroll
+                for (int e = 0; e < NB; ++e) {
+                    const bool on = mm != 0u;
+                    const int b = on ? __ffs(mm) - 1 + d_r : 0;
+                    mm &= mm - 1;
+                    const uint32_t orow = row ^ (1u << b);
+                    if (on) { k[e] = c.rowB[b][orow]; ld4(v + (((uint64_t)orow << KC) | lo0), y[e]); }
+                    else {
+                        k[e] = 0.0;
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) y[e][t] = 0.0;
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < NB; ++e)
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) acc[t] = fma(k[e], y[e][t], acc[t]);
+            }
+        }
+        if (valid) {
+            double2* o = reinterpret_cast<double2*>(Yt + rl * rs + (cl << 4) + ((uint32_t)lc << 2));
+            o[0] = make_double2(acc[0], acc[1]);
+            o[1] = make_double2(acc[2], acc[3]);
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: inner levels of the combined index m (popcount j), edges on inside bits from shared memory ----
+    for (int j = 0; j <= d; ++j) {
+        const uint32_t offD = hsidx[d * 32 + j];
+        const uint32_t units = hsidx[d * 32 + j + 1] - offD;
+        for (uint32_t u0 = (uint32_t)w * 8u; u0 < units; u0 += 64u) {
+            const bool valid = u0 + (uint32_t)lg < units;
+            const uint32_t m = hs[offD + min(u0 + (uint32_t)lg, units - 1u)];
+            const uint32_t rl = m >> d_c, cl = m & ((1u << d_c) - 1u);
+            const uint32_t row = (rH << d_r) | rl;
+            const uint32_t cA = (cH << d_c) | cl;
+            const uint32_t lo0 = (cA << 4) | ((uint32_t)lc << 2);
+            const uint32_t so = rl * rs + (cl << 4) + ((uint32_t)lc << 2);      // own tile in the shared block
+            double acc[4];
+            {
+                const double2* a2 = reinterpret_cast<const double2*>(Yt + so);
+                const double2 p0 = a2[0], p1 = a2[1];
+                acc[0] = p0.x; acc[1] = p0.y; acc[2] = p1.x; acc[3] = p1.y;
+            }
+            uint32_t mm = m;                             // inside bits: popcount j in every lane group
+            while (mm) {
+                const int p = __ffs(mm) - 1;
+                mm &= mm - 1;
+                double y[4];
+                if (p < d_c) {                           // column-block bit: source tile (rl, cl - bit), rate vector of the source columns
+                    const double2* y2 = reinterpret_cast<const double2*>(Yt + (so ^ (16u << p)));
+                    const double2 p0 = y2[0], p1 = y2[1];
+                    y[0] = p0.x; y[1] = p0.y; y[2] = p1.x; y[3] = p1.y;
+                    double r[4];
+                    ld4(c.colA[4 + p] + (lo0 ^ (16u << p)), r);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) acc[t] = fma(r[t], y[t], acc[t]);
+                } else {                                 // row bit: source tile (rl - bit, cl), one scalar rate
+                    const int b = p - d_c;
+                    const double2* y2 = reinterpret_cast<const double2*>(Yt + (so - (rs << b)));
+                    const double2 p0 = y2[0], p1 = y2[1];
+                    y[0] = p0.x; y[1] = p0.y; y[2] = p1.x; y[3] = p1.y;
+                    const double k = c.rowB[b][row ^ (1u << b)];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) acc[t] = fma(k, y[t], acc[t]);
+                }
+            }
+            double val[4];
+            tile_tail<false, false>(c, row, lo0, lane, acc, val);
+            if (valid) {
+                double2* o = reinterpret_cast<double2*>(Yt + so);
+                o[0] = make_double2(val[0], val[1]);
+                o[1] = make_double2(val[2], val[3]);
+                st4(v + (((uint64_t)row << KC) | lo0), val[0], val[1], val[2], val[3]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Second version of the blocked forward solve (MMH_BLOCK=2).  NOT YET RUN ON A GPU (written after the round's GPU
+// budget was spent; version 1 above is tested).  Version 1 measured slower than the tile kernel (forward solve 90 ->
+// 109 ms serial) although it halves the line reads: its phase 2 fetches the rate vectors of every inner-level tile
+// from global memory (two dependent latencies per round, ten rounds per block).  Here everything phase 2 needs is
+// staged in shared memory once per block: the rate rows of the 4 + d_c inside column bits and the diagonal part dA
+// over the block's columns, the diagonal part dB and the inside row-bit rates over the block's rows.
+//   shared layout (doubles): Yt[BLK_STATES] | Rc[(4 + d_c)][rs] | dAc[rs] | dBr[nr] | Rr[d_r][nr]   (rs = 2^(d_c+4), nr = 2^d_r)
+constexpr int BLK2_SMEM_DOUBLES = BLK_STATES + 8 * 256 + 256 + 256 + 8 * 256;
+
+__device__ __forceinline__ void tile_tail_fwd_s(const double* __restrict__ Rc, uint32_t rs, const double* __restrict__ dAc,
+                                                double dBv, uint32_t lcol, int lane, double (&acc)[4], double (&val)[4])
+{
+    const int lc = lane & 3;
+    double inv[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) inv[t] = 1.0 / (dAc[lcol + t] + dBv);
+    const double e0a = Rc[lcol], e0b = Rc[lcol + 2];                       // bit 0: 0 -> 1, 2 -> 3
+    const double e1a = Rc[rs + lcol], e1b = Rc[rs + lcol + 1];              // bit 1: 0 -> 2, 1 -> 3
+    double w0[4] = {0.0, 0.0, 0.0, 0.0}, w1a[4] = {0.0, 0.0, 0.0, 0.0}, w1b[4] = {0.0, 0.0, 0.0, 0.0};
+    const int pl = __popc(lc);
+    if (pl == 1) {
+        const int q = lc == 2;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) w0[t] = Rc[(2 + q) * rs + (lcol ^ (4u << q)) + t];
+    } else if (lc == 3) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { w1a[t] = Rc[2 * rs + (lcol ^ 4u) + t]; w1b[t] = Rc[3 * rs + (lcol ^ 8u) + t]; }
+    }
+    auto fin = [&]() {
+        val[0] = acc[0] * inv[0];
+        val[1] = fma(e0a, val[0], acc[1]) * inv[1];
+        val[2] = fma(e1a, val[0], acc[2]) * inv[2];
+        val[3] = fma(e0b, val[2], fma(e1b, val[1], acc[3])) * inv[3];
+    };
+    fin();
+#pragma unroll
+    for (int t = 0; t < 4; ++t) acc[t] = fma(w0[t], __shfl_sync(0xffffffffu, val[t], lane & ~3), acc[t]);
+    fin();
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const double p = __shfl_xor_sync(0xffffffffu, val[t], 1);
+        const double q = __shfl_xor_sync(0xffffffffu, val[t], 2);
+        acc[t] = fma(w1b[t], q, fma(w1a[t], p, acc[t]));
+    }
+    fin();
+}
+
+__global__ void __launch_bounds__(256, 3)
+k_solve_block_fwd2(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs, const uint32_t* __restrict__ hs,
+                   const uint32_t* __restrict__ hsidx, double* __restrict__ S)
+{
+    extern __shared__ double smem2[];
+    __shared__ TileCtx ctx;
+    const Item sg = segs[blockIdx.x];
+    const SpaceDev& sp = spaces[sg.space];
+    tile_ctx_build(ctx, sp, S, threadIdx.x);
+    __syncthreads();
+    const TileCtx& c = ctx;
+    const int KC = c.KC, KR = c.KR;
+    int d_c, d_r;
+    block_dims(KC, KR, d_c, d_r);
+    const int d = d_c + d_r, kbA = KC - 4 - d_c, kbB = KR - d_r;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, lc = lane & 3, lg = lane >> 2;
+    const uint32_t lA = sg.a & 255u, lB = (sg.a >> 8) & 255u;
+    const uint32_t offA = hsidx[kbA * 32 + lA];
+    const uint32_t offB = hsidx[kbB * 32 + lB], nBo = hsidx[kbB * 32 + lB + 1] - offB;
+    const uint32_t iA = sg.b / nBo, iB = sg.b - iA * nBo;
+    const uint32_t cH = hs[offA + iA], rH = hs[offB + iB];
+    const uint32_t rs = 1u << (d_c + 4), nr = 1u << d_r;
+    const uint32_t ntile = 1u << d;
+    const uint32_t colbase = cH << (d_c + 4), rowbase = rH << d_r;
+    double* Yt = smem2;
+    double* Rc = Yt + BLK_STATES;
+    double* dAc = Rc + (size_t)(4 + d_c) * rs;
+    double* dBr = dAc + rs;
+    double* Rr = dBr + nr;
+    double* v = S + sp.y_off;
+    // ---- phase 0: stage the block's rates and diagonal parts ----
+    for (uint32_t i = threadIdx.x; i < (uint32_t)(4 + d_c) * rs; i += blockDim.x) {
+        const uint32_t q = i / rs, jcol = i - q * rs;
+        Rc[i] = c.colA[q][colbase + jcol];
+    }
+    for (uint32_t i = threadIdx.x; i < rs; i += blockDim.x) dAc[i] = c.dA[colbase + i];
+    for (uint32_t i = threadIdx.x; i < nr; i += blockDim.x) dBr[i] = c.dB[rowbase + i];
+    for (uint32_t i = threadIdx.x; i < (uint32_t)d_r * nr; i += blockDim.x) {
+        const uint32_t b = i / nr, rl = i - b * nr;
+        Rr[i] = c.rowB[b][rowbase + rl];                  // rate of adding row bit b at (source) row rl
+    }
+    // ---- phase 1: as in version 1 ----
+    for (uint32_t m0 = (uint32_t)w * 8u; m0 < ntile; m0 += 64u) {
+        const uint32_t m = min(m0 + (uint32_t)lg, ntile - 1u);
+        const bool valid = m0 + (uint32_t)lg < ntile;
+        const uint32_t rl = m >> d_c, cl = m & ((1u << d_c) - 1u);
+        const uint32_t row = rowbase | rl;
+        const uint32_t lo0 = colbase | (cl << 4) | ((uint32_t)lc << 2);
+        const uint32_t s0 = (row << KC) | lo0;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        tile_rhs<false>(sp, spaces, S, KC, KR, row, lo0, acc);
+        {
+            constexpr int NB = TILE_NBA;
+            uint32_t mm = cH;
+            while (mm) {
+                double r[NB][4], y[NB][4];
+#pragma unroll
+                for (int e = 0; e < NB; ++e) {
+                    const bool on = mm != 0u;
+                    const int a = on ? __ffs(mm) + 3 + d_c : 4;
+                    mm &= mm - 1;
+                    const uint32_t bit = 1u << a;
+                    if (on) { ld4(c.colA[a] + (lo0 ^ bit), r[e]); ld4(v + (s0 ^ bit), y[e]); }
+                    else {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) { r[e][t] = 0.0; y[e][t] = 0.0; }
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < NB; ++e)
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) acc[t] = fma(r[e][t], y[e][t], acc[t]);
+            }
+        }
+        {
+            constexpr int NB = TILE_NBB;
+            uint32_t mm = rH;
+            while (mm) {
+                double y[NB][4], k[NB];
+#pragma unroll
+                for (int e = 0; e < NB; ++e) {
+                    const bool on = mm != 0u;
+                    const int b = on ? __ffs(mm) - 1 + d_r : 0;
+                    mm &= mm - 1;
+                    const uint32_t orow = row ^ (1u << b);
+                    if (on) { k[e] = c.rowB[b][orow]; ld4(v + (((uint64_t)orow << KC) | lo0), y[e]); }
+                    else {
+                        k[e] = 0.0;
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) y[e][t] = 0.0;
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < NB; ++e)
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) acc[t] = fma(k[e], y[e][t], acc[t]);
+            }
+        }
+        if (valid) {
+            double2* o = reinterpret_cast<double2*>(Yt + rl * rs + (cl << 4) + ((uint32_t)lc << 2));
+            o[0] = make_double2(acc[0], acc[1]);
+            o[1] = make_double2(acc[2], acc[3]);
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: inner levels, shared memory only ----
+    for (int j = 0; j <= d; ++j) {
+        const uint32_t offD = hsidx[d * 32 + j];
+        const uint32_t units = hsidx[d * 32 + j + 1] - offD;
+        for (uint32_t u0 = (uint32_t)w * 8u; u0 < units; u0 += 64u) {
+            const bool valid = u0 + (uint32_t)lg < units;
+            const uint32_t m = hs[offD + min(u0 + (uint32_t)lg, units - 1u)];
+            const uint32_t rl = m >> d_c, cl = m & ((1u << d_c) - 1u);
+            const uint32_t lcol = (cl << 4) | ((uint32_t)lc << 2);               // column inside the block
+            const uint32_t so = rl * rs + lcol;                                  // own tile in the shared block
+            double acc[4];
+            {
+                const double2* a2 = reinterpret_cast<const double2*>(Yt + so);
+                const double2 p0 = a2[0], p1 = a2[1];
+                acc[0] = p0.x; acc[1] = p0.y; acc[2] = p1.x; acc[3] = p1.y;
+            }
+            uint32_t mm = m;
+            while (mm) {
+                const int p = __ffs(mm) - 1;
+                mm &= mm - 1;
+                if (p < d_c) {
+                    const uint32_t scol = lcol ^ (16u << p);                     // source columns (bit cleared)
+                    const double* ys = Yt + rl * rs + scol;
+                    const double* rr = Rc + (size_t)(4 + p) * rs + scol;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) acc[t] = fma(rr[t], ys[t], acc[t]);
+                } else {
+                    const int b = p - d_c;
+                    const uint32_t srl = rl ^ (1u << b);                         // source row (bit cleared)
+                    const double* ys = Yt + srl * rs + lcol;
+                    const double k = Rr[(size_t)b * nr + srl];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) acc[t] = fma(k, ys[t], acc[t]);
+                }
+            }
+            double val[4];
+            tile_tail_fwd_s(Rc, rs, dAc, dBr[rl], lcol, lane, acc, val);
+            if (valid) {
+                double2* o = reinterpret_cast<double2*>(Yt + so);
+                o[0] = make_double2(val[0], val[1]);
+                o[1] = make_double2(val[2], val[3]);
+                st4(v + (((uint64_t)(rowbase | rl) << KC) | colbase | lcol), val[0], val[1], val[2], val[3]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Adjoint tile solve of a pair with the group-B marginal statistics fused in.  The adjoint pass already holds, for
 // every state s and every row bit b not in s, the value x[s + b]; with y[s] (one more 32-byte load) the lane adds
 //     stB[1+b][uB] += sum_uA y[s] x[s + b]      stB[0][uB] += sum_uA x[s] y[s]
