@@ -668,7 +668,8 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
     if (const char* e = std::getenv("MMH_BLOCK")) h->block_version = std::atoi(e);
-    CK(cudaFuncSetAttribute(k_solve_block_fwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BLK2_SMEM_DOUBLES * sizeof(double))));
+    if (h->block_version == 2)
+        CK(cudaFuncSetAttribute(k_solve_block_fwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BLK2_SMEM_DOUBLES * sizeof(double))));
     CK(cudaFuncSetAttribute(k_solve_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
     CK(cudaFuncSetAttribute(k_solve_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
     CK(cudaFuncSetAttribute(k_finish<MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIN_SMEM));
