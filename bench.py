@@ -99,80 +99,190 @@ class ClockSampler:
 
 # ---- CPU baseline (reference algorithm, NumPy restatement) ------------------------------------------------
 def _cpu_one(args):
+    """One row through the reference algorithm; returns its time and its result (kept for the parity check)."""
     from oracle import reference_restated as rr
-    th, dp, dm, row = args
+    i, th, dp, dm, row = args
     t = time.perf_counter()
-    rr.patient_value_grad(th, dp, dm, row, want_grad=True)
-    return time.perf_counter() - t
+    r = rr.patient_value_grad(th, dp, dm, row, want_grad=True)
+    dt = time.perf_counter() - t
+    if r is None:
+        return i, dt, 0.0, None
+    is0, lp, g, gdp, gdm = r
+    return i, dt, float(lp), np.concatenate([np.asarray(g, dtype=float).ravel(), np.asarray(gdp, dtype=float).ravel(),
+                                             np.asarray(gdm, dtype=float).ravel()])
 
 
-def cpu_sample_rows(dat, max_bits):
+def row_strata(dat):
+    """(type, k) of every row and the reference's work estimate W = sum over the row's spaces of
+    N_eff * k_eff^2 * (k_eff + 1) ((k+1) Jacobi sweeps of ~k^2 passes over N_eff states)."""
     n = (dat.shape[1] - 3) // 2
-    typ = dat[:, -1]
-    bits = np.where(typ == 3, dat[:, :2 * n + 1].astype(np.int64).sum(axis=1),
-                    np.where(typ == 2, dat[:, 1:2 * n:2].astype(np.int64).sum(axis=1) + 1,
-                             dat[:, 0:2 * n + 1:2].astype(np.int64).sum(axis=1)))
-    return np.nonzero(bits <= max_bits)[0], bits
+    typ = dat[:, -1].astype(np.int64)
+    pt = dat[:, 0:2 * n:2].astype(np.int64).sum(axis=1)
+    mt = dat[:, 1:2 * n:2].astype(np.int64).sum(axis=1)
+    seed = dat[:, 2 * n].astype(np.int64)
+
+    def w(k):
+        k = np.maximum(k, 0).astype(np.float64)
+        return np.exp2(k) * k * k * (k + 1.0)
+    k = np.where(typ == 3, pt + mt + 1, np.where(typ == 2, mt + 1, pt + seed))
+    W = np.where(typ == 3, w(pt + mt) + w(mt) + w(pt), w(k))          # joint + both second-phase spaces (upper bound for order 1/2)
+    W = np.where((typ < 0) | (typ > 3), 0.0, W)
+    return typ, k, W
 
 
-def cpu_baseline(d, budget_s, max_bits=11, rows_limit=None):
-    """Time the reference algorithm (oracle/reference_restated.py: per-event Kronecker shuffles, (k+1) Jacobi
-    sweeps) on all host cores over a bounded sample: rows in dataset order whose lattice has <= 2^max_bits
-    states, as many as fit in the time budget."""
+def row_passes(dat):
+    """P = sum over the row's spaces of k_eff^2 (k_eff + 1): the number of vector passes behind W (W = N_eff * P per space)."""
+    n = (dat.shape[1] - 3) // 2
+    typ = dat[:, -1].astype(np.int64)
+    pt = dat[:, 0:2 * n:2].astype(np.int64).sum(axis=1).astype(np.float64)
+    mt = dat[:, 1:2 * n:2].astype(np.int64).sum(axis=1).astype(np.float64)
+    seed = dat[:, 2 * n].astype(np.float64)
+    p = lambda k: k * k * (k + 1.0)
+    P = np.where(typ == 3, p(pt + mt) + p(mt) + p(pt), np.where(typ == 2, p(mt + 1), p(pt + seed)))
+    return np.where((typ < 0) | (typ > 3), 0.0, P)
+
+
+def _cost_model(timed):
+    """cpu seconds of a row ~ c0 + c_pass * P + c_elem * W (P = vector passes, W = passes x elements): non-negative
+    least squares on the per-stratum means, relative residuals.  The per-pass term keeps the interpreter overhead of
+    the small lattices out of the per-element cost that the extrapolation to the big ones rests on."""
+    from scipy.optimize import nnls
+    vals = [v for v in timed.values() if v[0] > 0 and v[1] > 0]
+    t = np.array([v[1] / v[0] for v in vals])
+    A = np.array([[1.0, v[3] / v[0], v[2] / v[0]] for v in vals])
+    coef, _ = nnls(A / t[:, None], np.ones(len(vals)))
+    return float(coef[0]), float(coef[1]), float(coef[2])
+
+
+def cpu_baseline(d, budget_s, per_stratum=24, seed=0):
+    """Time the reference algorithm (oracle/reference_restated.py: per-event Kronecker shuffles, (k+1) Jacobi sweeps)
+    on all host cores over a STRATIFIED sample of the workload: rows grouped by (type, k), cheapest strata first,
+    up to `per_stratum` rows each, until the time budget is spent; the strata that were not reached (the 2^k tail,
+    hours of NumPy per row) are extrapolated with the survey's work estimate W at the cost per unit of W measured on
+    the two most expensive strata that were timed.  Returns the extrapolated whole-workload throughput and the
+    per-row results of the sample (for the parity check against the GPU)."""
     import multiprocessing as mp
     dat = d["dat"]
     n = (dat.shape[1] - 3) // 2
     ep = d["eval_point"]
     n_tot = n + 1
     th, dp, dm = ep[:n_tot * n_tot].reshape(n_tot, n_tot), ep[n_tot * n_tot:n_tot * (n_tot + 1)], ep[n_tot * (n_tot + 1):]
-    idx, bits = cpu_sample_rows(dat, max_bits)
-    share_rows = idx.shape[0] / dat.shape[0]
-    if rows_limit:
-        idx = idx[:rows_limit]
+    typ, k, W = row_strata(dat)
+    P = row_passes(dat)
+    rng = np.random.default_rng(seed)
+    strata = {}
+    for t in range(4):
+        for kk in np.unique(k[typ == t]):
+            rows = np.nonzero((typ == t) & (k == kk))[0]
+            strata[(t, int(kk))] = rows
+    order = sorted(strata, key=lambda key: float(W[strata[key][0]]))
     cores = os.cpu_count() or 1
-    done = 0
-    t0 = time.perf_counter()
+    t_start = time.perf_counter()
+    timed = {}                                  # stratum -> (rows timed, cpu seconds)
+    res_idx, res_lp, res_g = [], [], []
     with mp.get_context("fork").Pool(cores) as pool:
-        it = pool.imap(_cpu_one, ((th, dp, dm, dat[i]) for i in idx), chunksize=4)
-        for _ in it:
-            done += 1
-            if rows_limit is None and time.perf_counter() - t0 > budget_s:
+        for key in order:
+            if time.perf_counter() - t_start > budget_s:
                 break
+            rows = strata[key]
+            take = rows if rows.shape[0] <= per_stratum else rng.choice(rows, per_stratum, replace=False)
+            # expensive strata: only as many rows as the remaining budget allows (at least two, one per core at most)
+            if timed:
+                c0, cp, unit = _cost_model(timed)
+                est = c0 + cp * float(P[take[0]]) + unit * float(W[take[0]])
+                left = max(budget_s - (time.perf_counter() - t_start), 0.0)
+                fit = int(left * cores / max(est, 1e-9))
+                if fit < 2:
+                    break
+                take = take[:max(2, min(take.shape[0], fit, 2 * cores))]
+            cpu = 0.0
+            for i, dt, lp, g in pool.imap_unordered(_cpu_one, ((int(i), th, dp, dm, dat[i]) for i in take), chunksize=1):
+                cpu += dt
+                if g is not None:
+                    res_idx.append(i); res_lp.append(lp); res_g.append(g)
+            timed[key] = (int(take.shape[0]), cpu, float(W[take].sum()), float(P[take].sum()))
         pool.terminate()
-    el = time.perf_counter() - t0
-    used = idx[:done]
-    states = float(np.exp2(bits[used]).sum())
-    return {"value": done / el, "unit": "patients/s", "cores": cores, "kind": "port",
-            "sample": f"first {done} rows (dataset order) with lattice <= 2^{max_bits} states "
-                      f"({100 * share_rows:.1f}% of rows qualify); reference algorithm = oracle/reference_restated.py "
-                      f"(NumPy restatement: JAX is not installable here), multiprocessing over rows, {el:.1f} s",
-            "rows": int(done), "seconds": el, "states_per_s": states / el, "row_index": used}
+    wall = time.perf_counter() - t_start
+    # extrapolation: measured strata scale by their row count; the others by W at the cost per unit of W of the two
+    # most expensive strata that were timed
+    c0, cp, unit = _cost_model(timed)
+    cpu_total, cpu_measured_part, rows_measured = 0.0, 0.0, 0
+    for key, rows in strata.items():
+        if key in timed:
+            cnt, cpu = timed[key][:2]
+            cpu_total += cpu / cnt * rows.shape[0]
+            cpu_measured_part += cpu / cnt * rows.shape[0]
+            rows_measured += rows.shape[0]
+        else:
+            cpu_total += c0 * rows.shape[0] + cp * float(P[rows].sum()) + unit * float(W[rows].sum())
+    n_rows = int(sum(v[0] for v in timed.values()))
+    est_wall = cpu_total / cores
+    kmax = {t: max((kk for (tt, kk) in timed if tt == t), default=-1) for t in range(4)}
+    return {"value": dat.shape[0] / est_wall, "unit": "patients/s", "cores": cores, "kind": "port",
+            "extrapolated": True,
+            "sample": f"stratified by (type, k): {n_rows} rows from {len(timed)} of {len(strata)} strata (every stratum up to "
+                      f"k = {kmax} per type), {wall:.1f} s wall on {cores} cores; reference algorithm = "
+                      f"oracle/reference_restated.py (NumPy restatement: JAX is not installable here), multiprocessing over "
+                      f"rows; whole-workload time = measured strata scaled by their row counts ({rows_measured} rows, "
+                      f"{cpu_measured_part / cores:.1f} s) + the remaining strata extrapolated with "
+                      f"cpu-s per row = {c0:.2e} + {cp:.2e} * P + {unit:.2e} * W (non-negative least squares on the stratum means; "
+                      f"P = sum k_eff^2 (k_eff+1) passes, W = sum N_eff k_eff^2 (k_eff+1)); total {est_wall:.0f} s",
+            "rows": n_rows, "seconds": wall, "extrapolated_seconds_full_workload": est_wall,
+            "measured_share_of_rows": rows_measured / max(dat.shape[0], 1),
+            "row_index": np.asarray(res_idx, dtype=np.int64), "row_logp": np.asarray(res_lp),
+            "row_grad_sum": np.sum(res_g, axis=0) if res_g else None}
 
 
 def run_reference(args, rank, world):
+    """Reference arm: the reference algorithm on the host cores, same workload, same metric.  A step is one bounded
+    stratified sample (see cpu_baseline); the value is the whole-workload throughput extrapolated from it."""
     if rank != 0:
         return
     d = workload(args)
-    # calibrate the sample so that one step is ~8 s of all-core CPU work
-    cal = cpu_baseline(d, 6.0)
-    rows = max(8, int(cal["value"] * 8.0))
     for _ in range(args.warmup):
-        cpu_baseline(d, 0, rows_limit=max(8, rows // 8))
-    t = []
-    last = None
-    for _ in range(args.steps):
-        last = cpu_baseline(d, 0, rows_limit=rows)
+        cpu_baseline(d, 1.0, per_stratum=4)
+    t, last, vals = [], None, []
+    for s in range(args.steps):
+        last = cpu_baseline(d, args.ref_step_seconds, seed=s)
         t.append(last["seconds"])
-    val = last["rows"] * len(t) / sum(t)
+        vals.append(last["value"])
+    val = float(np.mean(vals))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "patients/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(t) / len(t),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(base_config(args), cpu_step="bounded sample of the workload's rows, see cpu_baseline.sample"),
+            "config": dict(base_config(args), cpu_step="one bounded stratified sample of the workload's rows per step; value = "
+                                                      "whole-workload patients/s extrapolated from it (cpu_baseline.sample)"),
             "cpu_baseline": {"value": val, "unit": "patients/s", "cores": last["cores"], "kind": "port",
-                             "sample": last["sample"]},
+                             "extrapolated": True, "sample": last["sample"]},
             "e2e": {"value": val, "unit": "patients/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def parity_vs_oracle(cb, dat, ep, device):
+    """The oracle's per-row results of the CPU sample against the CUDA path on the same rows of the bench dataset."""
+    from metmhn_b200 import Handle
+    rows = cb["row_index"]
+    if rows.shape[0] == 0:
+        return None
+    h = Handle(np.ascontiguousarray(dat[rows]), device=device)
+    lp = h.per_patient(ep)
+    s, g = h.eval_weighted(ep, 1.0, 1.0, want_grad=True)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        h.eval_weighted(ep, 1.0, 1.0, want_grad=True)
+    gpu_rate = rows.shape[0] * 3 / (time.perf_counter() - t0)
+    h.close()
+    ref_lp, ref_g = cb["row_logp"], cb["row_grad_sum"]
+    e_lp = float(np.max(np.abs(lp - ref_lp) / np.maximum(np.abs(ref_lp), 1e-300)))
+    scale = np.maximum(np.abs(ref_g), 1e-3 * np.max(np.abs(ref_g)))
+    e_g = float(np.max(np.abs(g - ref_g) / scale))
+    typ, k, _ = row_strata(dat[rows])
+    return {"rows_checked": int(rows.shape[0]), "max_lattice_bits": int(k.max()),
+            "logp_max_rel_err": e_lp, "grad_sum_max_rel_err": e_g,
+            "parity_max_rel_err": max(e_lp, e_g), "tolerance": 1e-10, "ok": bool(max(e_lp, e_g) <= 1e-10),
+            "against": "oracle/reference_restated.py on rows of THIS bench dataset (the stratified cpu_baseline sample)",
+            "gpu_same_rows_patients_per_s": gpu_rate}
 
 
 # ---- this repo's arm ---------------------------------------------------------------------------------------
@@ -244,7 +354,9 @@ def run_ours(args, rank, local_rank, world):
         s_host, g_host = ev.value_grad(ep, PERC_MET)
     barrier()
     wall_e2e = max_over_ranks(time.perf_counter() - t0)
-    assert abs(s_host - result_dev[0]) <= 1e-12 * abs(s_host)
+    # the two call paths (device-resident step, host API) must give the same numbers: reported, not asserted
+    e2e_vs_device = float(max(abs(s_host - result_dev[0]) / abs(s_host),
+                              np.max(np.abs(g_host - result_dev[1:])) / np.max(np.abs(g_host))))
 
     # per-class device times (CUDA events on the launching stream) for the roofline
     ev.handle.set_profile(True)
@@ -296,6 +408,9 @@ def run_ours(args, rank, local_rank, world):
                     "h2d_bytes_per_step": int(ev.npar * 8), "d2h_bytes_per_step": int((ev.npar + 1) * 8),
                     "api": "ShardedEvaluator.value_grad(params_host, perc_met) -> (score, grad) host"},
             "gpu_launches": int(launches * args.steps),
+            "e2e_vs_device_max_rel_diff": e2e_vs_device,
+            "allreduce": ("in-library ncclAllReduce on the handle's stream (mmh_comm_init)" if ev.in_library_reduce
+                          else "none (one GPU)"),
             "roofline": {"kernel": kernels[top], "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": ach / peaks["hbm_gbs"],
                          "traffic": (traffic_per_state[top] * states / 1e9) if top in traffic_per_state else None,
@@ -318,17 +433,14 @@ def run_ours(args, rank, local_rank, world):
         }
         if world == 1 and not args.no_cpu:
             cb = cpu_baseline(d, args.cpu_seconds)
-            rows = cb.pop("row_index")
-            from metmhn_b200 import Handle
-            hs = Handle(np.ascontiguousarray(dat[rows]), device=local_rank)
-            hs.value_grad(ep, PERC_MET)
-            t0 = time.perf_counter()
-            for _ in range(5):
-                hs.value_grad(ep, PERC_MET)
-            cb["gpu_same_sample_value"] = rows.shape[0] * 5 / (time.perf_counter() - t0)
-            hs.close()
-            cb.pop("seconds", None)
+            par = parity_vs_oracle(cb, dat, ep, local_rank)
+            for key in ("row_index", "row_logp", "row_grad_sum", "seconds"):
+                cb.pop(key, None)
             line["cpu_baseline"] = cb
+            if par is not None:
+                line["parity"] = par
+                line["parity_max_rel_err"] = par["parity_max_rel_err"]
+                line["rows_checked"] = par["rows_checked"]
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -345,15 +457,35 @@ def main():
     ap.add_argument("--patients", type=int, default=100000)
     ap.add_argument("--chunk-bytes", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    ap.add_argument("--ref-step-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
-    run_ours(args, rank, local_rank, world)
+    try:
+        if args.impl == "reference":
+            run_reference(args, rank, world)
+        else:
+            run_ours(args, rank, local_rank, world)
+    except BaseException:
+        # torchrun swallows the traceback of a failing rank: say which rank, why, and what the library last reported
+        import traceback
+        msg = traceback.format_exc()
+        try:
+            from metmhn_b200 import _lib
+            msg += f"mmh_last_error: {_lib.lib().mmh_last_error().decode('utf-8', 'replace')}\n"
+        except Exception:
+            pass
+        sys.stderr.write(f"[bench rank {rank}/{world}] FAILED\n{msg}")
+        sys.stderr.flush()
+        try:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", f"bench_error_rank{rank}.txt"), "w") as f:
+                f.write(msg)
+        except OSError:
+            pass
+        raise
 
 
 if __name__ == "__main__":

@@ -35,6 +35,7 @@ extern "C" {
 #define MMH_ECUDA     (-2)   /* CUDA runtime failure or no device */
 #define MMH_ENOMEM    (-3)
 #define MMH_ETOOLARGE (-4)   /* a patient's restricted state space exceeds the supported size */
+#define MMH_ENCCL     (-5)   /* NCCL missing (libnccl.so.2 could not be loaded) or a NCCL call failed */
 
 #define MMH_MAX_MUT    28    /* events excluding seeding (LUAD uses 28) */
 #define MMH_MAX_BITS   26    /* largest restricted lattice (bits) one space may have */
@@ -95,6 +96,32 @@ int mmh_set_profile(mmh_handle* h, int on);
 /* Per-row log-likelihoods of the last evaluation's parameters (test hook).  Rows with an
  * unknown type get 0. */
 int mmh_per_patient(mmh_handle* h, const double* params, double* logp);
+
+/* ---- multi-GPU: one handle per GPU, the shard results are summed by ONE in-library ncclAllReduce ----------
+ * The reference sums per-patient results (regularized_optimization.py:187-267); with the dataset sharded over
+ * handles that are evaluated with the GLOBAL class weights (mmh_eval_weighted / mmh_eval_device) the only
+ * exchange is the sum of 1 + (n+1)(n+3) doubles.  libnccl.so.2 is loaded with dlopen() on first use, so the
+ * library itself has no link-time NCCL dependency.
+ *
+ * One process per GPU (torchrun / MPI): rank 0 calls mmh_nccl_unique_id() and ships the 128 bytes to the other
+ * ranks by whatever means it has; every rank then calls mmh_comm_init() (collective, blocks until all ranks
+ * joined).  From then on every mmh_eval_weighted / mmh_eval_device / mmh_value_grad / mmh_value on that handle
+ * ends with ncclAllReduce(sum) of the result ON THE HANDLE'S STREAM, i.e. ordered with the evaluation that
+ * produced it and with the next one that overwrites it; all ranks must make the same sequence of calls. */
+#define MMH_NCCL_ID_BYTES 128
+int mmh_nccl_unique_id(char id[MMH_NCCL_ID_BYTES]);
+int mmh_comm_init(mmh_handle* h, const char id[MMH_NCCL_ID_BYTES], int nranks, int rank);
+int mmh_comm_destroy(mmh_handle* h);
+
+/* One process, several GPUs: the rows are partitioned over `n_devices` devices by a longest-processing-time
+ * cost model (same as metmhn_b200/sharded.py), one handle per device, ncclCommInitAll, and every evaluation
+ * runs on all devices concurrently and ends with the all-reduce.  Same result layout as mmh_value_grad. */
+typedef struct mmh_multi mmh_multi;
+int mmh_multi_create(mmh_multi** out, int n_mut, const int8_t* dat, int64_t n_dat, int64_t row_stride,
+                     const int* device_ids, int n_devices, int64_t chunk_bytes);
+int mmh_multi_value_grad(mmh_multi* m, const double* params, double perc_met, double* score, double* grad);
+int mmh_multi_value(mmh_multi* m, const double* params, double perc_met, double* score);
+void mmh_multi_destroy(mmh_multi* m);
 
 int mmh_stats(mmh_handle* h, mmh_stats_t* out);
 void mmh_destroy(mmh_handle* h);

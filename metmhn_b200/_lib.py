@@ -14,12 +14,15 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MMH_LIB") or os.path.join(_HERE, "libmetmhn_b200.so")   # MMH_LIB: A/B builds of the same library
 
-MMH_OK, MMH_EINVAL, MMH_ECUDA, MMH_ENOMEM, MMH_ETOOLARGE = 0, -1, -2, -3, -4
+MMH_OK, MMH_EINVAL, MMH_ECUDA, MMH_ENOMEM, MMH_ETOOLARGE, MMH_ENCCL = 0, -1, -2, -3, -4, -5
+NCCL_ID_BYTES = 128
 MAX_MUT = 28
 
 EXPORTS = ("mmh_create", "mmh_value_grad", "mmh_value", "mmh_eval_weighted", "mmh_eval_device", "mmh_sync",
            "mmh_set_profile", "mmh_per_patient",
-           "mmh_stats", "mmh_destroy", "mmh_last_error", "mmh_measure_fp64_tflops")
+           "mmh_stats", "mmh_destroy", "mmh_last_error", "mmh_measure_fp64_tflops",
+           "mmh_nccl_unique_id", "mmh_comm_init", "mmh_comm_destroy",
+           "mmh_multi_create", "mmh_multi_value_grad", "mmh_multi_value", "mmh_multi_destroy")
 
 
 class Stats(C.Structure):
@@ -60,8 +63,17 @@ def lib():
     L.mmh_destroy.restype = None
     L.mmh_last_error.restype = C.c_char_p
     L.mmh_measure_fp64_tflops.argtypes = [C.c_int, dp]
+    L.mmh_nccl_unique_id.argtypes = [C.c_char_p]
+    L.mmh_comm_init.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
+    L.mmh_comm_destroy.argtypes = [C.c_void_p]
+    L.mmh_multi_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int64, C.c_int64,
+                                   C.POINTER(C.c_int), C.c_int, C.c_int64]
+    L.mmh_multi_value_grad.argtypes = [C.c_void_p, dp, C.c_double, dp, dp]
+    L.mmh_multi_value.argtypes = [C.c_void_p, dp, C.c_double, dp]
+    L.mmh_multi_destroy.argtypes = [C.c_void_p]
+    L.mmh_multi_destroy.restype = None
     for name in EXPORTS:
-        if name not in ("mmh_destroy", "mmh_last_error"):
+        if name not in ("mmh_destroy", "mmh_last_error", "mmh_multi_destroy"):
             getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -146,10 +158,70 @@ class Handle:
         d["k_hist"] = {t: {k: int(s.k_hist[t][k]) for k in range(64) if s.k_hist[t][k]} for t in range(4)}
         return d
 
+    def comm_init(self, unique_id: bytes, nranks: int, rank: int):
+        """Attach an NCCL communicator (collective over all ranks): from now on every evaluation on this handle
+        ends with an in-library all-reduce of the result on the handle's stream."""
+        if len(unique_id) != NCCL_ID_BYTES:
+            raise MetMHNError(MMH_EINVAL, "the NCCL unique id has 128 bytes")
+        check(lib().mmh_comm_init(self._h, unique_id, int(nranks), int(rank)))
+
+    def comm_destroy(self):
+        if self._h:
+            check(lib().mmh_comm_destroy(self._h))
+
     def close(self):
         if self._h:
             lib().mmh_destroy(self._h)
             self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def nccl_unique_id() -> bytes:
+    """128 opaque bytes from ncclGetUniqueId; rank 0 creates them and ships them to the other ranks."""
+    buf = C.create_string_buffer(NCCL_ID_BYTES)
+    check(lib().mmh_nccl_unique_id(buf))
+    return buf.raw
+
+
+class MultiHandle:
+    """One process, several GPUs (mmh_multi_*): rows partitioned by the cost model, one in-library all-reduce."""
+
+    def __init__(self, dat, devices, chunk_bytes=0):
+        dat = np.ascontiguousarray(np.asarray(dat), dtype=np.int8)
+        if dat.ndim != 2 or dat.shape[1] < 5 or (dat.shape[1] - 3) % 2:
+            raise MetMHNError(MMH_EINVAL, "dat must be (n_dat, 2n+3) int8")
+        self.n_mut = (dat.shape[1] - 3) // 2
+        self.n_tot = self.n_mut + 1
+        self.npar = self.n_tot * (self.n_tot + 2)
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        self._m = C.c_void_p()
+        check(lib().mmh_multi_create(C.byref(self._m), self.n_mut, dat.ctypes.data_as(C.c_void_p), dat.shape[0],
+                                     dat.shape[1], devs, len(devices), int(chunk_bytes)))
+
+    def value_grad(self, params, perc_met):
+        p = np.ascontiguousarray(np.asarray(params, dtype=np.float64).ravel())
+        if p.shape[0] != self.npar:
+            raise MetMHNError(MMH_EINVAL, f"params must have {self.npar} entries")
+        score = C.c_double()
+        grad = np.empty(self.npar)
+        check(lib().mmh_multi_value_grad(self._m, _dptr(p), float(perc_met), C.byref(score), _dptr(grad)))
+        return score.value, grad
+
+    def value(self, params, perc_met):
+        p = np.ascontiguousarray(np.asarray(params, dtype=np.float64).ravel())
+        score = C.c_double()
+        check(lib().mmh_multi_value(self._m, _dptr(p), float(perc_met), C.byref(score)))
+        return score.value
+
+    def close(self):
+        if self._m:
+            lib().mmh_multi_destroy(self._m)
+            self._m = C.c_void_p()
 
     def __del__(self):
         try:

@@ -9,6 +9,8 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+
 #include "../../include/metmhn_b200.h"
 #include "mmh_device.cuh"
 
@@ -25,7 +27,8 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
     do {                                                                                      \
         cudaError_t e_ = (call);                                                              \
         if (e_ != cudaSuccess)                                                                \
-            return fail(MMH_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));       \
+            return fail(e_ == cudaErrorMemoryAllocation ? MMH_ENOMEM : MMH_ECUDA,             \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                  \
     } while (0)
 
 namespace {
@@ -91,6 +94,8 @@ struct mmh_handle {
     std::vector<cudaEvent_t> evpool;
     uint32_t max_joints = 0;
     mmh_stats_t st{};
+    void* comm = nullptr;                        // ncclComm_t once mmh_comm_init ran: every evaluation ends with an all-reduce
+    bool comm_owned = true;
 };
 
 // pairs whose adjoint solve also produces the group-B statistics (k_solve_tile_adjb); needs splitA/splitB
@@ -162,6 +167,7 @@ static int build_patient(const int8_t* row, int n, int32_t pid, PatientPlan& pp,
     const int typ = row[2 * n + 2];
     pp.sp.clear();
     cls = 255;
+    if (typ < 0 || typ > 3) return MMH_OK;       // rows of an unknown type contribute nothing (regularized_optimization.py:187-254)
     for (int c = 0; c < 2 * n + 1; ++c)
         if (row[c] != 0 && row[c] != 1) return fail(MMH_EINVAL, "genotype entries must be 0 or 1");
     auto base = [&](Kind k) {
@@ -248,6 +254,9 @@ static int build_patient(const int8_t* row, int n, int32_t pid, PatientPlan& pp,
     return MMH_OK;
 }
 
+static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_dat, int64_t row_stride,
+                       int device, int64_t chunk_bytes);
+
 extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_t n_dat, int64_t row_stride,
                           int device, int64_t chunk_bytes)
 {
@@ -258,6 +267,15 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
         return fail(MMH_ECUDA, "mmh_create: no usable CUDA device (this library has no CPU fallback)");
     CK(cudaSetDevice(device));
     mmh_handle* h = new mmh_handle();
+    const int rc = create_impl(h, n_mut, dat, n_dat, row_stride, device, chunk_bytes);
+    if (rc != MMH_OK) { const std::string keep = g_err; mmh_destroy(h); g_err = keep; return rc; }   // nothing leaks on a failed create
+    *out = h;
+    return MMH_OK;
+}
+
+static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_dat, int64_t row_stride,
+                       int device, int64_t chunk_bytes)
+{
     h->device = device; h->n = n_mut; h->n_tot = n_mut + 1; h->n_dat = n_dat;
     h->st.n_dat = n_dat;
     const int n = n_mut;
@@ -270,7 +288,7 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
         const int8_t* row = dat + p * row_stride;
         h->n_em += row[2 * n];
         int rc = build_patient(row, n, (int32_t)p, pats[(size_t)p], h->st, cnt_dm2, cls[(size_t)p]);
-        if (rc != MMH_OK) { delete h; return rc; }
+        if (rc != MMH_OK) return rc;
     }
     h->st.n_em = h->n_em;
     h->st.alg_bytes = 32.0 * h->st.states_value_grad;
@@ -675,7 +693,6 @@ extern "C" int mmh_create(mmh_handle** out, int n_mut, const int8_t* dat, int64_
     CK(cudaFuncSetAttribute(k_finish<MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIN_SMEM));
     CK(cudaFuncSetAttribute(k_finish<MAXG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIN_SMEM));
     h->st.scratch_bytes = (double)max_scratch * 8.0 * h->ns;
-    *out = h;
     return MMH_OK;
 }
 
@@ -908,6 +925,108 @@ static void class_weights(const mmh_handle* h, double perc_met, double& w0, doub
     w1 = w / n_full;
 }
 
+
+// ---- NCCL (loaded lazily with dlopen: the library has no link-time dependency on it) ------------------------
+namespace {
+struct ncclUniqueIdT { char internal[MMH_NCCL_ID_BYTES]; };
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueIdT*) = nullptr;
+    int (*CommInitRank)(void**, int, ncclUniqueIdT, int) = nullptr;
+    int (*CommInitAll)(void**, int, const int*) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+constexpr int NCCL_DOUBLE = 8, NCCL_SUM = 0;      // ncclFloat64, ncclSum (nccl.h; stable since NCCL 2.0)
+
+NcclApi& nccl()
+{
+    static NcclApi api = [] {
+        NcclApi a;
+        const char* names[] = {std::getenv("MMH_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) {
+            if (!nm) continue;
+            a.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);   // an already loaded libnccl.so.2 (e.g. torch's) is reused
+            if (a.lib) break;
+        }
+        if (!a.lib) return a;
+        auto sym = [&](const char* n) { return dlsym(a.lib, n); };
+        a.GetUniqueId = (decltype(a.GetUniqueId))sym("ncclGetUniqueId");
+        a.CommInitRank = (decltype(a.CommInitRank))sym("ncclCommInitRank");
+        a.CommInitAll = (decltype(a.CommInitAll))sym("ncclCommInitAll");
+        a.CommDestroy = (decltype(a.CommDestroy))sym("ncclCommDestroy");
+        a.AllReduce = (decltype(a.AllReduce))sym("ncclAllReduce");
+        a.GroupStart = (decltype(a.GroupStart))sym("ncclGroupStart");
+        a.GroupEnd = (decltype(a.GroupEnd))sym("ncclGroupEnd");
+        a.GetErrorString = (decltype(a.GetErrorString))sym("ncclGetErrorString");
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommInitAll && a.CommDestroy && a.AllReduce && a.GroupStart &&
+               a.GroupEnd && a.GetErrorString;
+        return a;
+    }();
+    return api;
+}
+int nccl_fail(const char* what, int rc)
+{
+    return fail(MMH_ENCCL, std::string(what) + ": " + (nccl().GetErrorString ? nccl().GetErrorString(rc) : "NCCL error"));
+}
+}  // namespace
+
+#define NK(call)                                                            \
+    do {                                                                    \
+        int r_ = (call);                                                    \
+        if (r_ != 0) return nccl_fail(#call, r_);                           \
+    } while (0)
+
+extern "C" int mmh_nccl_unique_id(char id[MMH_NCCL_ID_BYTES])
+{
+    if (!id) return fail(MMH_EINVAL, "mmh_nccl_unique_id: null argument");
+    if (!nccl().ok) return fail(MMH_ENCCL, "libnccl.so.2 could not be loaded (set MMH_NCCL_LIB)");
+    ncclUniqueIdT u;
+    NK(nccl().GetUniqueId(&u));
+    std::memcpy(id, u.internal, MMH_NCCL_ID_BYTES);
+    return MMH_OK;
+}
+
+extern "C" int mmh_comm_init(mmh_handle* h, const char id[MMH_NCCL_ID_BYTES], int nranks, int rank)
+{
+    if (!h || !id || nranks < 1 || rank < 0 || rank >= nranks) return fail(MMH_EINVAL, "mmh_comm_init: bad arguments");
+    if (!nccl().ok) return fail(MMH_ENCCL, "libnccl.so.2 could not be loaded (set MMH_NCCL_LIB)");
+    if (h->comm) return fail(MMH_EINVAL, "mmh_comm_init: the handle already has a communicator");
+    CK(cudaSetDevice(h->device));
+    ncclUniqueIdT u;
+    std::memcpy(u.internal, id, MMH_NCCL_ID_BYTES);
+    void* comm = nullptr;
+    NK(nccl().CommInitRank(&comm, nranks, u, rank));
+    h->comm = comm;
+    h->comm_owned = true;
+    return MMH_OK;
+}
+
+extern "C" int mmh_comm_destroy(mmh_handle* h)
+{
+    if (!h) return fail(MMH_EINVAL, "mmh_comm_destroy: null argument");
+    if (h->comm) {
+        cudaSetDevice(h->device);
+        cudaStreamSynchronize(h->stream);
+        if (h->comm_owned) nccl().CommDestroy(h->comm);
+        h->comm = nullptr;
+    }
+    return MMH_OK;
+}
+
+// the shard results add up: one all-reduce of the result vector on the stream that produced it
+static int reduce_result(mmh_handle* h, size_t len)
+{
+    if (!h->comm) return MMH_OK;
+    NK(nccl().AllReduce(h->d_out, h->d_out, len, NCCL_DOUBLE, NCCL_SUM, h->comm, h->stream));
+    CK(cudaEventRecord(h->ev1, h->stream));          // the device time of an evaluation includes its collective
+    return MMH_OK;
+}
+
 extern "C" int mmh_eval_weighted(mmh_handle* h, const double* params, double w_type0, double w_other,
                                  int want_grad, double* out_host, double* out_dev)
 {
@@ -917,6 +1036,8 @@ extern "C" int mmh_eval_weighted(mmh_handle* h, const double* params, double w_t
     int rc = run_eval(h, h->d_params, w_type0, w_other, want_grad);
     if (rc != MMH_OK) return rc;
     const size_t len = want_grad ? (size_t)h->n_tot * (h->n_tot + 2) + 1 : 1;
+    rc = reduce_result(h, len);
+    if (rc != MMH_OK) return rc;
     if (out_dev) CK(cudaMemcpyAsync(out_dev, h->d_out, len * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     if (out_host) CK(cudaMemcpyAsync(h->h_out, h->d_out, len * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -933,6 +1054,8 @@ extern "C" int mmh_eval_device(mmh_handle* h, const double* d_params, double w_t
     int rc = run_eval(h, d_params, w_type0, w_other, want_grad);
     if (rc != MMH_OK) return rc;
     const size_t len = want_grad ? (size_t)h->n_tot * (h->n_tot + 2) + 1 : 1;
+    rc = reduce_result(h, len);
+    if (rc != MMH_OK) return rc;
     CK(cudaMemcpyAsync(d_out, h->d_out, len * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     return MMH_OK;
 }
@@ -997,6 +1120,7 @@ extern "C" void mmh_destroy(mmh_handle* h)
 {
     if (!h) return;
     cudaSetDevice(h->device);
+    mmh_comm_destroy(h);
     cudaFree(h->d_spaces); cudaFree(h->d_lists); cudaFree(h->d_items); cudaFree(h->d_hs); cudaFree(h->d_hsidx); cudaFree(h->d_ctr); cudaFree(h->d_cls);
     cudaFree(h->d_cnt); cudaFree(h->d_par); cudaFree(h->d_params); cudaFree(h->d_logp);
     for (int q = 0; q < mmh_handle::NS; ++q) {
@@ -1013,6 +1137,121 @@ extern "C" void mmh_destroy(mmh_handle* h)
     for (cudaEvent_t e : h->evpool) cudaEventDestroy(e);
     for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
     delete h;
+}
+
+
+// ---- one process, several GPUs ---------------------------------------------------------------------------
+struct mmh_multi {
+    std::vector<mmh_handle*> hs;
+    int n_tot = 0;
+    int64_t n_dat = 0, n_em = 0;
+};
+
+// work estimate of a row: lattice states times (bits + 8), summed over the row's spaces (metmhn_b200/sharded.py)
+static double row_cost(const int8_t* row, int n)
+{
+    int pt = 0, mt = 0;
+    for (int e = 0; e < n; ++e) { pt += row[2 * e] != 0; mt += row[2 * e + 1] != 0; }
+    const int seed = row[2 * n] != 0, typ = row[2 * n + 2];
+    auto c = [](int k) { return std::ldexp(1.0, k) * (k + 8); };
+    if (typ == 0 || typ == 1) return c(pt + seed);
+    if (typ == 2) return c(mt + 1);
+    if (typ == 3) return c(pt + mt) + c(pt) + c(mt);
+    return 1.0;
+}
+
+extern "C" void mmh_multi_destroy(mmh_multi* m)
+{
+    if (!m) return;
+    for (mmh_handle* h : m->hs) mmh_destroy(h);
+    delete m;
+}
+
+extern "C" int mmh_multi_create(mmh_multi** out, int n_mut, const int8_t* dat, int64_t n_dat, int64_t row_stride,
+                                const int* device_ids, int n_devices, int64_t chunk_bytes)
+{
+    if (!out || !dat || !device_ids || n_devices < 1 || n_mut < 1 || n_mut > MMH_MAX_MUT || n_dat < 0 || row_stride < 2 * n_mut + 3)
+        return fail(MMH_EINVAL, "mmh_multi_create: bad arguments");
+    if (n_devices > 1 && !nccl().ok) return fail(MMH_ENCCL, "libnccl.so.2 could not be loaded (set MMH_NCCL_LIB)");
+    const int n = n_mut, width = 2 * n + 3;
+    // longest-processing-time assignment, deterministic (ties: lower row index first, lower device first)
+    std::vector<int64_t> order((size_t)n_dat);
+    std::vector<double> cost((size_t)n_dat);
+    for (int64_t p = 0; p < n_dat; ++p) { order[(size_t)p] = p; cost[(size_t)p] = row_cost(dat + p * row_stride, n); }
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return cost[(size_t)a] > cost[(size_t)b]; });
+    std::vector<double> load((size_t)n_devices, 0.0);
+    std::vector<std::vector<int8_t>> shard((size_t)n_devices);
+    int64_t n_em = 0;
+    for (int64_t p : order) {
+        int best = 0;
+        for (int d = 1; d < n_devices; ++d) if (load[(size_t)d] < load[(size_t)best]) best = d;
+        load[(size_t)best] += cost[(size_t)p];
+        const int8_t* row = dat + p * row_stride;
+        shard[(size_t)best].insert(shard[(size_t)best].end(), row, row + width);
+        n_em += row[2 * n];
+    }
+    mmh_multi* m = new mmh_multi();
+    m->n_tot = n + 1; m->n_dat = n_dat; m->n_em = n_em;
+    for (int d = 0; d < n_devices; ++d) {
+        mmh_handle* h = nullptr;
+        static const int8_t none = 0;
+        const int8_t* rows = shard[(size_t)d].empty() ? &none : shard[(size_t)d].data();
+        const int rc = mmh_create(&h, n_mut, rows, (int64_t)(shard[(size_t)d].size() / width), width, device_ids[d], chunk_bytes);
+        if (rc != MMH_OK) { const std::string keep = g_err; mmh_multi_destroy(m); g_err = keep; return rc; }
+        m->hs.push_back(h);
+    }
+    if (n_devices > 1) {
+        std::vector<void*> comms((size_t)n_devices, nullptr);
+        const int rc = nccl().CommInitAll(comms.data(), n_devices, device_ids);
+        if (rc != 0) { mmh_multi_destroy(m); return nccl_fail("ncclCommInitAll", rc); }
+        for (int d = 0; d < n_devices; ++d) { m->hs[(size_t)d]->comm = comms[(size_t)d]; m->hs[(size_t)d]->comm_owned = true; }
+    }
+    *out = m;
+    return MMH_OK;
+}
+
+static int multi_eval(mmh_multi* m, const double* params, double perc_met, int want_grad, double* out)
+{
+    const double n_em = (double)m->n_em, n_nm = (double)m->n_dat - n_em;      // regularized_optimization.py:256-262
+    const double w = (n_em * n_nm != 0.0) ? perc_met * n_nm / ((1.0 - perc_met) * n_em) : 1.0;
+    const double n_full = w * n_em + n_nm, w0 = 1.0 / n_full, w1 = w / n_full;
+    const size_t npar = (size_t)m->n_tot * (m->n_tot + 2), len = want_grad ? npar + 1 : 1;
+    for (mmh_handle* h : m->hs) {
+        CK(cudaSetDevice(h->device));
+        CK(cudaMemcpyAsync(h->d_params, params, npar * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        const int rc = run_eval(h, h->d_params, w0, w1, want_grad);
+        if (rc != MMH_OK) return rc;
+    }
+    if (m->hs.size() > 1) {
+        NK(nccl().GroupStart());
+        for (mmh_handle* h : m->hs)
+            NK(nccl().AllReduce(h->d_out, h->d_out, len, NCCL_DOUBLE, NCCL_SUM, h->comm, h->stream));
+        NK(nccl().GroupEnd());
+    }
+    mmh_handle* h0 = m->hs[0];
+    CK(cudaSetDevice(h0->device));
+    CK(cudaMemcpyAsync(h0->h_out, h0->d_out, len * sizeof(double), cudaMemcpyDeviceToHost, h0->stream));
+    for (mmh_handle* h : m->hs) { CK(cudaSetDevice(h->device)); CK(cudaStreamSynchronize(h->stream)); }
+    std::memcpy(out, h0->h_out, len * sizeof(double));
+    return MMH_OK;
+}
+
+extern "C" int mmh_multi_value_grad(mmh_multi* m, const double* params, double perc_met, double* score, double* grad)
+{
+    if (!m || !params || !score || !grad) return fail(MMH_EINVAL, "mmh_multi_value_grad: null argument");
+    const size_t npar = (size_t)m->n_tot * (m->n_tot + 2);
+    std::vector<double> buf(npar + 1);
+    const int rc = multi_eval(m, params, perc_met, 1, buf.data());
+    if (rc != MMH_OK) return rc;
+    *score = buf[0];
+    std::memcpy(grad, buf.data() + 1, npar * sizeof(double));
+    return MMH_OK;
+}
+
+extern "C" int mmh_multi_value(mmh_multi* m, const double* params, double perc_met, double* score)
+{
+    if (!m || !params || !score) return fail(MMH_EINVAL, "mmh_multi_value: null argument");
+    return multi_eval(m, params, perc_met, 0, score);
 }
 
 extern "C" const char* mmh_last_error(void) { return g_err.c_str(); }

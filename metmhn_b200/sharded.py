@@ -78,18 +78,32 @@ class ShardedEvaluator:
         self.handle = None
         self._dev_out = None
         self._dev_par = None
+        self.in_library_reduce = False
         if local_eval is None:
             from ._lib import Handle
             self.handle = Handle(self.shard, device=device, chunk_bytes=chunk_bytes)
             local_eval = self._cuda_eval
+            if world > 1:
+                self._attach_comm()
         self.local_eval = local_eval
+
+    def _attach_comm(self):
+        """Give the handle its own NCCL communicator (id from rank 0, shipped through the torch.distributed group
+        that launched the ranks): the all-reduce then runs inside the library on the handle's stream, ordered with
+        the evaluation that produced the result and with the next one that overwrites it."""
+        import torch.distributed as dist
+        from ._lib import nccl_unique_id
+        box = [nccl_unique_id() if self.rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=self.group)
+        self.handle.comm_init(box[0], self.world, self.rank)
+        self.in_library_reduce = True
 
     def _cuda_eval(self, params, w0, w1, want_grad):
         s, g = self.handle.eval_weighted(params, w0, w1, want_grad=want_grad)
         return np.concatenate([[s], g]) if want_grad else np.array([s])
 
     def _reduce(self, vec):
-        if self.world <= 1:
+        if self.world <= 1 or self.in_library_reduce:
             return vec
         import torch
         import torch.distributed as dist
@@ -119,11 +133,9 @@ class ShardedEvaluator:
         return self._dev_par, self._dev_out
 
     def step_device(self, w0, w1, want_grad=True):
-        """One evaluation with parameters and result resident in HBM (+ the all-reduce when world > 1)."""
+        """One evaluation with parameters and result resident in HBM.  With world > 1 the library ends the
+        evaluation with its own ncclAllReduce on the handle's stream, so `out` is never touched by two streams."""
         par, out = self.device_buffers()
         self.handle.eval_device(par.data_ptr(), w0, w1, out.data_ptr(), want_grad)
         self.handle.sync()
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
         return out
