@@ -17,7 +17,7 @@
 using namespace mmh;
 
 static constexpr int RED_SLICES = 32;            // first stage of the gradient-partials reduction
-static constexpr size_t RB_SMEM = (size_t)RB_STATES * sizeof(double);
+static constexpr size_t BLK_SMEM = (size_t)BLKW * BLK_DOUBLES * sizeof(double);
 static constexpr size_t FIN_SMEM = (size_t)(NACC * NR * NR + FIN_WARPS * NR * 33) * sizeof(double);
 
 static thread_local std::string g_err;
@@ -42,10 +42,7 @@ struct ChunkPlan {
     Range setup, setup_wide, diag, pre, main_small, sec_small, logp, joints, st_a, st_ar, st_b, pf_lo, pf_hi, fin;
     bool wide = false;                           // some group has more than MAXT bits
     std::vector<Range> main_lv, sec_lv;          // big-tier segments per popcount level (generic kernel)
-    std::vector<Range> main_lvt, sec_lvt;        // big-tier tiles per level (tiled kernel)
-    std::vector<Range> main_lvr, sec_lvr;        // big-tier row blocks per row level (row-block kernel)
-    std::vector<Range> main_lvt_adj, main_lvt_adjb;  // adjoint pass of the main tiled spaces: plain / with fused B statistics
-    std::vector<Range> main_lvb;                 // forward pass of pairs with the two-dimensional blocked kernel (MMH_BLOCK=1)
+    std::vector<Range> main_lvb, sec_lvb;        // big-tier blocks per outer level (blocked kernel, mmh_blk.cuh)
     uint64_t scratch = 0;                        // doubles
 };
 
@@ -65,11 +62,7 @@ struct mmh_handle {
     Item* d_items = nullptr;
     uint32_t* d_hs = nullptr;
     uint32_t* d_hsidx = nullptr;                 // [bits][level] -> first entry of that popcount level in d_hs
-    uint32_t* d_ctr = nullptr;                   // MMH_SMLOCAL=1: per-launch, per-SM work queue counters
-    uint32_t ctr_launches = 0;                   // fat tile launches per evaluation (capacity of d_ctr)
-    int nsm = 0, smlocal = 0;
-    int block_version = 0;                       // MMH_BLOCK: 1 = blocked forward solve (tested), 2 = with staged rates (untested)
-    uint32_t smlocal_min = 0;                    // launches with more items than this use the SM-local kernel
+    int nsm = 0;
     uint8_t* d_cls = nullptr;
     double* d_cnt = nullptr;
     EvalPar* d_par = nullptr;
@@ -98,26 +91,6 @@ struct mmh_handle {
     bool comm_owned = true;
 };
 
-// pairs whose adjoint solve also produces the group-B statistics (k_solve_tile_adjb); needs splitA/splitB
-static bool fused_b(const SpaceDev& s)
-{
-    static const bool off = [] { const char* e = std::getenv("MMH_FUSE_B"); return e && std::atoi(e) == 0; }();
-    return !off && s.kind == K_JOINT && !s.splitA && !s.splitB && s.KA >= 4 && (int)s.KA + (int)s.KB >= BIGK;
-}
-// number of partial tables: per column-block level lA one per chunk of 32 column blocks; base[lA] = first slot
-static uint32_t adjb_slots(int kbA, uint32_t* base)
-{
-    uint32_t n = 0;
-    double c = 1.0;                                     // C(kbA, lA)
-    for (int lA = 0; lA <= kbA; ++lA) {
-        if (base) base[lA] = n;
-        const uint64_t nA = (uint64_t)(c + 0.5);
-        n += (uint32_t)std::max<uint64_t>(1, (nA + 31) / 32);
-        c = c * (kbA - lA) / (lA + 1);
-    }
-    return n;
-}
-
 static uint64_t space_scratch(SpaceDev& s, uint64_t off)
 {
     const uint64_t NA = 1ull << s.KA, NB = 1ull << s.KB, N = NA * NB;
@@ -129,6 +102,8 @@ static uint64_t space_scratch(SpaceDev& s, uint64_t off)
     auto table = [&](int KG, uint8_t& split) {
         if (KG <= max_full) { split = 0; return take((uint64_t)NR << KG); }
         split = (uint8_t)((KG + 1) / 2);             // rate(i,u) = T1[i][u_lo] * T2[i][u_hi] + full special-row vectors
+        // big single-tumour spaces: the low table covers exactly the eight column bits of the blocked solve
+        if (s.kind != K_JOINT && s.kind != K_PRE && KG >= BIGK) split = (uint8_t)BLK_CB;
         return take(((uint64_t)NR << split) + ((uint64_t)NR << (KG - split)) + ((has_diag_tables ? 3ull : 1ull) << KG));
     };
     s.splitA = s.splitB = 0;
@@ -146,7 +121,6 @@ static uint64_t space_scratch(SpaceDev& s, uint64_t off)
         const uint64_t capB = std::max<uint64_t>(8, (2ull << 20) / ((s.KB + 1) * NB));
         s.slices = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(256, capA), std::max<uint64_t>(1, NB / 128));
         s.slicesB = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(256, capB), std::max<uint64_t>(1, NA / 2048));
-        if (fused_b(s)) s.slicesB = adjb_slots(s.KA - 4, nullptr);     // one partial table per (lA, column chunk)
         s.stA = take((s.KA + 1) * NA);
         s.stB = take((s.KB + 1) * NB);
         s.stP = take((uint64_t)s.slices * (s.KA + 1) * NA);
@@ -403,26 +377,17 @@ static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_da
                     for (uint32_t lb = 0; lb < nlo; ++lb) items.push_back({i, lb, hb});
             }
         ck.diag.cnt = (uint32_t)(items.size() - ck.diag.off);
-        // spaces the tiled solve kernel takes (must agree with tiled_space() on the device side)
-        auto tiled = [&](const SpaceDev& s) {
-            if (bits(s) < BIGK || s.kind == K_PRE) return false;
-            if (s.kind == K_JOINT) return !s.splitA && !s.splitB && s.KA >= 4;
-            return s.splitA >= 4;
-        };
-        // experimental (profiles/NOTES.md): the row-block kernel is only used when MMH_ROWBLOCK=1
-        static const bool use_rowblock = [] { const char* e = std::getenv("MMH_ROWBLOCK"); return e && std::atoi(e) != 0; }();
-        auto rowblock = [&](const SpaceDev& s) {
-            return use_rowblock && tiled(s) && (s.kind == K_JOINT ? s.KA : s.splitA) <= RB_MAXKC;
-        };
+        auto blocked = [&](const SpaceDev& s) { return blocked_space(s); };
+        // generic big-tier kernel (pairs with split tables or 1-2 PT bits): segments of 32-state blocks per popcount level
         auto levels_of = [&](auto pred, std::vector<Range>& lv) {
             int maxkh = -1;
-            for (uint32_t i = 0; i < ck.nspaces; ++i) if (pred(sp[i]) && bits(sp[i]) >= BIGK && !tiled(sp[i])) maxkh = std::max(maxkh, bits(sp[i]) - 7);
+            for (uint32_t i = 0; i < ck.nspaces; ++i) if (pred(sp[i]) && bits(sp[i]) >= BIGK && !blocked(sp[i])) maxkh = std::max(maxkh, bits(sp[i]) - 7);
             if (maxkh < 0) return;
             lv.resize(maxkh + 1);
             for (int l = 0; l <= maxkh; ++l) {
                 lv[l].off = items.size();
                 for (uint32_t i = 0; i < ck.nspaces; ++i) {
-                    if (!pred(sp[i]) || bits(sp[i]) < BIGK || tiled(sp[i])) continue;
+                    if (!pred(sp[i]) || bits(sp[i]) < BIGK || blocked(sp[i])) continue;
                     const int kh = bits(sp[i]) - 7;          // blocks of 128 states
                     if (l > kh) continue;
                     need_hs(kh);
@@ -433,134 +398,29 @@ static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_da
                 lv[l].cnt = (uint32_t)(items.size() - lv[l].off);
             }
         };
-        // tiled kernel: rows x column blocks, one launch per level lA + lB; a CTA item is up to TILES_PER_CTA warp
-        // tiles (8 rows x 16 columns) of one (lA, lB) split
-        auto levels_of_t = [&](auto pred, std::vector<Range>& lv) {
+        // blocked kernel: one launch per level of the K-12 outer bits; an item is a run of blocks of one space, one
+        // block per warp at a time.  Thin levels get one block per warp, fat ones up to 8 rounds per CTA.
+        auto levels_of_b = [&](auto pred, std::vector<Range>& lv) {
             int maxl = -1;
-            auto dims = [&](const SpaceDev& s, int& kbA, int& kbB) {
-                if (s.kind == K_JOINT) { kbA = s.KA - 4; kbB = s.KB; }
-                else { kbA = s.splitA - 4; kbB = s.KA - s.splitA; }
-            };
             for (uint32_t i = 0; i < ck.nspaces; ++i)
-                if (pred(sp[i]) && tiled(sp[i]) && !rowblock(sp[i])) { int a, b; dims(sp[i], a, b); maxl = std::max(maxl, a + b); }
+                if (pred(sp[i]) && blocked(sp[i])) maxl = std::max(maxl, bits(sp[i]) - BLK_CB - BLK_SB);
             if (maxl < 0) return;
             lv.resize(maxl + 1);
             for (int l = 0; l <= maxl; ++l) {
                 lv[l].off = items.size();
-                // thin levels: one tile per warp (the launch is a single wave and its duration the latency of the
-                // tiles a warp runs back to back); fat levels: up to TILES_PER_CTA tiles per CTA
                 uint64_t total = 0;
                 for (int pass = 0; pass < 2; ++pass) {
-                    const uint64_t per_cta = total <= 8ull * 3 * 148 ? 8 : total <= 16ull * 3 * 148 ? 16 : TILES_PER_CTA;
+                    const uint32_t rounds = (uint32_t)std::min<uint64_t>(8, std::max<uint64_t>(1, total / ((uint64_t)BLKW * 148)));
+                    const uint32_t per_cta = rounds * BLKW;
                     for (uint32_t i = 0; i < ck.nspaces; ++i) {
-                        if (!pred(sp[i]) || !tiled(sp[i]) || rowblock(sp[i])) continue;
-                        int kbA, kbB;
-                        dims(sp[i], kbA, kbB);
-                        if (l > kbA + kbB) continue;
-                        need_hs(kbA); need_hs(kbB);
-                        for (int lA = std::max(0, l - kbB); lA <= std::min(kbA, l); ++lA) {
-                            const int lB = l - lA;
-                            const uint64_t nA = hs_lvl[kbA][lA + 1] - hs_lvl[kbA][lA];
-                            const uint64_t nB = hs_lvl[kbB][lB + 1] - hs_lvl[kbB][lB];
-                            const uint64_t T = nA * ((nB + 7) / 8);
-                            if (pass == 0) { total += T; continue; }
-                            for (uint64_t t0 = 0; t0 < T; t0 += per_cta)
-                                items.push_back({i, (uint32_t)lA | ((uint32_t)lB << 8) | ((uint32_t)std::min<uint64_t>(per_cta, T - t0) << 16), (uint32_t)t0});
-                        }
-                    }
-                }
-                lv[l].cnt = (uint32_t)(items.size() - lv[l].off);
-            }
-        };
-        // row-block kernel: one launch per ROW level; an item is up to RB_STATES >> KC rows of that level
-        auto levels_of_r = [&](auto pred, std::vector<Range>& lv) {
-            int maxl = -1;
-            auto dims = [&](const SpaceDev& s, int& kc, int& kr) {
-                if (s.kind == K_JOINT) { kc = s.KA; kr = s.KB; }
-                else { kc = s.splitA; kr = s.KA - s.splitA; }
-            };
-            for (uint32_t i = 0; i < ck.nspaces; ++i)
-                if (pred(sp[i]) && rowblock(sp[i])) { int kc, kr; dims(sp[i], kc, kr); maxl = std::max(maxl, kr); }
-            if (maxl < 0) return;
-            lv.resize(maxl + 1);
-            for (int l = 0; l <= maxl; ++l) {
-                lv[l].off = items.size();
-                for (uint32_t i = 0; i < ck.nspaces; ++i) {
-                    if (!pred(sp[i]) || !rowblock(sp[i])) continue;
-                    int kc, kr;
-                    dims(sp[i], kc, kr);
-                    if (l > kr) continue;
-                    need_hs(kc - 4); need_hs(kr);
-                    const uint32_t nB = hs_lvl[kr][l + 1] - hs_lvl[kr][l];
-                    const uint32_t rmax = std::max<uint32_t>(1u, (uint32_t)RB_STATES >> kc);
-                    for (uint32_t r0 = 0; r0 < nB; r0 += rmax)
-                        items.push_back({i, (uint32_t)l | (std::min<uint32_t>(rmax, nB - r0) << 8), r0});
-                }
-                lv[l].cnt = (uint32_t)(items.size() - lv[l].off);
-            }
-        };
-        // adjoint pass with fused group-B statistics: CTA = G row groups x C column blocks of one (lA, lB) split
-        auto levels_of_adjb = [&](std::vector<Range>& lv) {
-            int maxl = -1;
-            for (uint32_t i = 0; i < ck.nspaces; ++i)
-                if (fused_b(sp[i]) && !rowblock(sp[i])) maxl = std::max(maxl, (int)sp[i].KA - 4 + (int)sp[i].KB);
-            if (maxl < 0) return;
-            lv.resize(maxl + 1);
-            for (int l = 0; l <= maxl; ++l) {
-                lv[l].off = items.size();
-                for (uint32_t i = 0; i < ck.nspaces; ++i) {
-                    if (!fused_b(sp[i]) || rowblock(sp[i])) continue;
-                    const int kbA = sp[i].KA - 4, kbB = sp[i].KB;
-                    if (l > kbA + kbB) continue;
-                    need_hs(kbA); need_hs(kbB);
-                    uint32_t base[MMH_MAX_BITS + 1];
-                    adjb_slots(kbA, base);
-                    for (int lA = std::max(0, l - kbB); lA <= std::min(kbA, l); ++lA) {
-                        const int lB = l - lA;
-                        const uint32_t nA = hs_lvl[kbA][lA + 1] - hs_lvl[kbA][lA];
-                        const uint32_t nB = hs_lvl[kbB][lB + 1] - hs_lvl[kbB][lB];
-                        const uint32_t nBg = (nB + 7) / 8;
-                        uint32_t C = 32;
-                        if (nA < 32) { C = 1; while (C < nA) C <<= 1; }
-                        const uint32_t G = 32 / C, nch = nA < 32 ? 1 : (nA + 31) / 32;
-                        for (uint32_t jB = 0; jB < nBg; jB += G)
-                            for (uint32_t k = 0; k < nch; ++k)
-                                items.push_back({i, (uint32_t)lA | ((uint32_t)lB << 8), jB, k | ((base[lA] + k) << 16)});
-                    }
-                }
-                lv[l].cnt = (uint32_t)(items.size() - lv[l].off);
-            }
-        };
-        // experimental two-dimensional blocked forward solve (k_solve_block_fwd): pairs only, MMH_BLOCK=1
-        static const int block_version = [] { const char* e = std::getenv("MMH_BLOCK"); return e ? std::atoi(e) : 0; }();
-        static const bool use_block = block_version != 0;
-        auto blocked = [&](const SpaceDev& s) {
-            if (!use_block || !fused_b(s) || rowblock(s)) return false;
-            int d_c, d_r;
-            block_dims(s.KA, s.KB, d_c, d_r);
-            if (block_version == 2 && d_c > 4) return false;        // version 2 stages at most 8 rate rows of 256 columns
-            return d_c + d_r >= 4;
-        };
-        auto levels_of_b = [&](std::vector<Range>& lv) {
-            int maxl = -1;
-            for (uint32_t i = 0; i < ck.nspaces; ++i)
-                if (blocked(sp[i])) { int d_c, d_r; block_dims(sp[i].KA, sp[i].KB, d_c, d_r); maxl = std::max(maxl, (int)sp[i].KA - 4 - d_c + (int)sp[i].KB - d_r); }
-            if (maxl < 0) return;
-            lv.resize(maxl + 1);
-            for (int l = 0; l <= maxl; ++l) {
-                lv[l].off = items.size();
-                for (uint32_t i = 0; i < ck.nspaces; ++i) {
-                    if (!blocked(sp[i])) continue;
-                    int d_c, d_r;
-                    block_dims(sp[i].KA, sp[i].KB, d_c, d_r);
-                    const int kbA = sp[i].KA - 4 - d_c, kbB = sp[i].KB - d_r;
-                    if (l > kbA + kbB) continue;
-                    need_hs(kbA); need_hs(kbB); need_hs(d_c + d_r);
-                    for (int lA = std::max(0, l - kbB); lA <= std::min(kbA, l); ++lA) {
-                        const int lB = l - lA;
-                        const uint64_t nA = hs_lvl[kbA][lA + 1] - hs_lvl[kbA][lA];
-                        const uint64_t nB = hs_lvl[kbB][lB + 1] - hs_lvl[kbB][lB];
-                        for (uint64_t t = 0; t < nA * nB; ++t) items.push_back({i, (uint32_t)lA | ((uint32_t)lB << 8), (uint32_t)t});
+                        if (!pred(sp[i]) || !blocked(sp[i])) continue;
+                        const int ko = bits(sp[i]) - BLK_CB - BLK_SB;
+                        if (l > ko) continue;
+                        need_hs(ko);
+                        const uint32_t nblk = hs_lvl[ko][l + 1] - hs_lvl[ko][l];
+                        if (pass == 0) { total += nblk; continue; }
+                        for (uint32_t b0 = 0; b0 < nblk; b0 += per_cta)
+                            items.push_back({i, (uint32_t)l, b0, std::min<uint32_t>(per_cta, nblk - b0)});
                     }
                 }
                 lv[l].cnt = (uint32_t)(items.size() - lv[l].off);
@@ -568,13 +428,8 @@ static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_da
         };
         levels_of(is_main, ck.main_lv);
         levels_of(is_sec, ck.sec_lv);
-        levels_of_t([&](const SpaceDev& s) { return is_main(s) && !blocked(s); }, ck.main_lvt);
-        levels_of_b(ck.main_lvb);
-        levels_of_t([&](const SpaceDev& s) { return is_main(s) && !fused_b(s); }, ck.main_lvt_adj);
-        levels_of_adjb(ck.main_lvt_adjb);
-        levels_of_t(is_sec, ck.sec_lvt);
-        levels_of_r(is_main, ck.main_lvr);
-        levels_of_r(is_sec, ck.sec_lvr);
+        levels_of_b(is_main, ck.main_lvb);
+        levels_of_b(is_sec, ck.sec_lvb);
         ck.st_a.off = items.size();
         for (uint32_t i = 0; i < ck.nspaces; ++i)
             if (sp[i].kind == K_JOINT) {
@@ -594,7 +449,7 @@ static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_da
         ck.st_ar.cnt = (uint32_t)(items.size() - ck.st_ar.off);
         ck.st_b.off = items.size();
         for (uint32_t i = 0; i < ck.nspaces; ++i)
-            if (sp[i].kind == K_JOINT && !(fused_b(sp[i]) && !rowblock(sp[i])))
+            if (sp[i].kind == K_JOINT)
                 for (uint32_t sl = 0; sl < sp[i].slicesB; ++sl)
                     for (uint32_t u = 0; u < (1u << sp[i].KB); ++u) items.push_back({i, u, sl});
         ck.st_b.cnt = (uint32_t)(items.size() - ck.st_b.off);
@@ -634,15 +489,6 @@ static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_da
     cudaDeviceProp prop{};
     CK(cudaGetDeviceProperties(&prop, device));
     h->nsm = prop.multiProcessorCount;
-    if (const char* e = std::getenv("MMH_SMLOCAL")) h->smlocal = std::atoi(e) != 0;
-    h->smlocal_min = (uint32_t)(TILE_CTAS * h->nsm);
-    if (const char* e = std::getenv("MMH_SMLOCAL_MIN")) h->smlocal_min = (uint32_t)std::max(0, std::atoi(e));
-    if (h->smlocal) {
-        for (const ChunkPlan& ck : h->chunks)
-            for (const std::vector<Range>* lv : {&ck.main_lvt, &ck.sec_lvt, &ck.sec_lvt, &ck.main_lvt_adj})     // sec: both passes
-                for (const Range& r : *lv) if (r.cnt > h->smlocal_min) ++h->ctr_launches;
-        CK(cudaMalloc((void**)&h->d_ctr, std::max<size_t>(1, (size_t)h->ctr_launches * h->nsm) * sizeof(uint32_t)));
-    }
     h->fin_ctas = prop.multiProcessorCount * 3;          // three k_finish CTAs fit one SM (58 KB of shared memory each)
     auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
         cudaError_t e = cudaMalloc(dst, std::max<size_t>(bytes, 16));
@@ -685,11 +531,8 @@ static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_da
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
-    if (const char* e = std::getenv("MMH_BLOCK")) h->block_version = std::atoi(e);
-    if (h->block_version == 2)
-        CK(cudaFuncSetAttribute(k_solve_block_fwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BLK2_SMEM_DOUBLES * sizeof(double))));
-    CK(cudaFuncSetAttribute(k_solve_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
-    CK(cudaFuncSetAttribute(k_solve_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
+    CK(cudaFuncSetAttribute(k_blk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BLK_SMEM));
+    CK(cudaFuncSetAttribute(k_blk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BLK_SMEM));
     CK(cudaFuncSetAttribute(k_finish<MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIN_SMEM));
     CK(cudaFuncSetAttribute(k_finish<MAXG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIN_SMEM));
     h->st.scratch_bytes = (double)max_scratch * 8.0 * h->ns;
@@ -714,8 +557,6 @@ static int enqueue_eval(mmh_handle* h, const double* d_params, double w0, double
     };
     tick(5);
     k_prep<<<1, 1024, 0, st>>>(d_params, h->n_tot, h->d_par); ++launches;
-    if (h->smlocal && h->ctr_launches) CK(cudaMemsetAsync(h->d_ctr, 0, (size_t)h->ctr_launches * h->nsm * sizeof(uint32_t), st));
-    uint32_t ctr_idx = 0;
     if (want_grad) {
         CK(cudaMemsetAsync(h->d_partial, 0, (size_t)NS * h->fin_ctas * NACC * NR * NR * sizeof(double), st));
         CK(cudaMemsetAsync(h->d_diracc, 0, (size_t)NS * 2 * NR * sizeof(double), st));
@@ -761,28 +602,13 @@ static int enqueue_eval(mmh_handle* h, const double* d_params, double w0, double
                 ++launches;
             }
         };
-        auto bigt = [&](const std::vector<Range>& lv, bool adj) {
+        auto bigb = [&](const std::vector<Range>& lv, bool adj) {
             const int L = (int)lv.size();
             for (int q = 0; q < L; ++q) {
                 const Range& r = lv[adj ? L - 1 - q : q];
                 if (!r.cnt) continue;
-                if (h->smlocal && r.cnt > h->smlocal_min && ctr_idx < h->ctr_launches) {
-                    uint32_t* ctr = h->d_ctr + (size_t)ctr_idx++ * h->nsm;
-                    const uint32_t grid = std::min<uint32_t>(r.cnt, (uint32_t)(TILE_CTAS * h->nsm));
-                    if (adj) k_solve_tile_sm<true><<<grid, 256, 0, st>>>(sp, h->d_items + r.off, r.cnt, h->d_hs, h->d_hsidx, S, ctr, (uint32_t)h->nsm);
-                    else     k_solve_tile_sm<false><<<grid, 256, 0, st>>>(sp, h->d_items + r.off, r.cnt, h->d_hs, h->d_hsidx, S, ctr, (uint32_t)h->nsm);
-                } else if (adj) k_solve_tile<true><<<r.cnt, 256, 0, st>>>(sp, h->d_items + r.off, h->d_hs, h->d_hsidx, S);
-                else     k_solve_tile<false><<<r.cnt, 256, 0, st>>>(sp, h->d_items + r.off, h->d_hs, h->d_hsidx, S);
-                ++launches;
-            }
-        };
-        auto bigr = [&](const std::vector<Range>& lv, bool adj) {
-            const int L = (int)lv.size();
-            for (int q = 0; q < L; ++q) {
-                const Range& r = lv[adj ? L - 1 - q : q];
-                if (!r.cnt) continue;
-                if (adj) k_solve_rows<true><<<r.cnt, RB_THREADS, RB_SMEM, st>>>(sp, h->d_items + r.off, h->d_hs, h->d_hsidx, S);
-                else     k_solve_rows<false><<<r.cnt, RB_THREADS, RB_SMEM, st>>>(sp, h->d_items + r.off, h->d_hs, h->d_hsidx, S);
+                if (adj) k_blk<true><<<r.cnt, BLKW * 32, BLK_SMEM, st>>>(sp, h->d_items + r.off, h->d_hs, h->d_hsidx, S);
+                else     k_blk<false><<<r.cnt, BLKW * 32, BLK_SMEM, st>>>(sp, h->d_items + r.off, h->d_hs, h->d_hsidx, S);
                 ++launches;
             }
         };
@@ -793,23 +619,15 @@ static int enqueue_eval(mmh_handle* h, const double* d_params, double w0, double
         tick(1);
         small(ck.pre, false); small4(ck.pre4, false);
         small(ck.main_small, false); small4(ck.main_small4, false);
-        big(ck.main_lv, false); bigt(ck.main_lvt, false); bigr(ck.main_lvr, false);
-        for (const Range& r : ck.main_lvb) {
-            if (!r.cnt) continue;
-            if (h->block_version == 2)
-                k_solve_block_fwd2<<<r.cnt, 256, BLK2_SMEM_DOUBLES * sizeof(double), st>>>(sp, h->d_items + r.off, h->d_hs, h->d_hsidx, S);
-            else
-                k_solve_block_fwd<<<r.cnt, 256, BLK_STATES * sizeof(double), st>>>(sp, h->d_items + r.off, h->d_hs, h->d_hsidx, S);
-            ++launches;
-        }
+        big(ck.main_lv, false); bigb(ck.main_lvb, false);
         small(ck.sec_small, false); small4(ck.sec_small4, false);
-        big(ck.sec_lv, false); bigt(ck.sec_lvt, false); bigr(ck.sec_lvr, false);
+        big(ck.sec_lv, false); bigb(ck.sec_lvb, false);
         tick(5);
         if (ck.logp.cnt) { k_logp<<<(ck.logp.cnt + 127) / 128, 128, 0, st>>>(sp, h->d_lists + ck.logp.off, ck.logp.cnt, S, h->d_logp); ++launches; }
         if (!want_grad) continue;
         tick(2);
         small(ck.sec_small, true); small4(ck.sec_small4, true);
-        big(ck.sec_lv, true); bigt(ck.sec_lvt, true); bigr(ck.sec_lvr, true);
+        big(ck.sec_lv, true); bigb(ck.sec_lvb, true);
         tick(5);
         if (ck.joints.cnt) {
             k_direct<<<(ck.joints.cnt + 255) / 256, 256, 0, st>>>(sp, h->d_lists + ck.joints.off, ck.joints.cnt, S, d_tdir);
@@ -818,13 +636,7 @@ static int enqueue_eval(mmh_handle* h, const double* d_params, double w0, double
         }
         tick(2);
         small(ck.main_small, true); small4(ck.main_small4, true);
-        big(ck.main_lv, true); bigt(ck.main_lvt_adj, true); bigr(ck.main_lvr, true);
-        for (int q = (int)ck.main_lvt_adjb.size() - 1; q >= 0; --q) {
-            const Range& r = ck.main_lvt_adjb[q];
-            if (!r.cnt) continue;
-            k_solve_tile_adjb<<<r.cnt, 256, 0, st>>>(sp, h->d_items + r.off, h->d_hs, h->d_hsidx, S);
-            ++launches;
-        }
+        big(ck.main_lv, true); bigb(ck.main_lvb, true);
         small(ck.pre, true); small4(ck.pre4, true);
         tick(3);
         if (ck.st_a.cnt) {
@@ -1121,7 +933,7 @@ extern "C" void mmh_destroy(mmh_handle* h)
     if (!h) return;
     cudaSetDevice(h->device);
     mmh_comm_destroy(h);
-    cudaFree(h->d_spaces); cudaFree(h->d_lists); cudaFree(h->d_items); cudaFree(h->d_hs); cudaFree(h->d_hsidx); cudaFree(h->d_ctr); cudaFree(h->d_cls);
+    cudaFree(h->d_spaces); cudaFree(h->d_lists); cudaFree(h->d_items); cudaFree(h->d_hs); cudaFree(h->d_hsidx); cudaFree(h->d_cls);
     cudaFree(h->d_cnt); cudaFree(h->d_par); cudaFree(h->d_params); cudaFree(h->d_logp);
     for (int q = 0; q < mmh_handle::NS; ++q) {
         cudaFree(h->d_scratch_s[q]);

@@ -13,6 +13,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "mmh_blk.cuh"
+
 namespace mmh {
 
 constexpr int NR      = 32;   // table rows per group (events 0..28, then the three special rows)
@@ -682,69 +684,6 @@ k_solve_big4(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs,
     else                for (uint32_t r = w; r < sg.b; r += nw) solve_block4<ADJ, 0>(sp, spaces, ctx, S, hs[sg.a + r], lane);
 }
 
-// ------------------------------------------------------------------------------------------
-// Tiled solve (big tier, K >= BIGK).  The lattice is viewed as rows x columns:
-//   pair            : columns = group A (KC = KA bits), rows = group B (KR = KB bits); an A-edge's rate is a column
-//                     vector T_A[ev][uA], a B-edge's rate one scalar T_B[ev][uB] per row
-//   product single  : columns = the K1 low bits, rows = the K2 high bits; every rate is a column factor T1[ev][lo]
-//                     times a row factor T2[ev][hi]
-// A warp solves 8 independent rows x 16 consecutive columns: lane = (row group, 4 columns); column bits 0,1 live in
-// the lane's registers, bits 2,3 in the four lanes of a row group (three sub-levels, 3 shuffles per state), all
-// higher bits read 128-byte lines of blocks finished by earlier launches.  The 8 rows of a tile have the same
-// popcount lB and share the column block cA (popcount lA), so every loop of the warp has a uniform trip count and
-// the column-rate loads of the 8 row groups hit the same line.  One launch per level lA + lB.
-constexpr int TILES_PER_CTA = 32;
-#ifndef TILE_CTAS
-#define TILE_CTAS 4            // resident CTAs per SM of k_solve_tile (64 registers; 3 measured 1.2 % slower)
-#endif
-#ifndef ADJB_CTAS
-#define ADJB_CTAS 3
-#endif
-#ifndef TILE_NBA
-#define TILE_NBA 2            // column-bit edges in flight per round
-#endif
-#ifndef TILE_NBB
-#define TILE_NBB 3            // row-bit edges in flight per round
-#endif
-
-struct TileCtx {
-    const double* colA[MAXG];          // column bit q: column factor of its rate (T_A[ev] or T1[ev])
-    const double* rowA[MAXG];          // product only: row factor T2[ev] of column bit q
-    const double* rowB[MAXG];          // row bit b: row factor (T_B[ev] or T2[ev])
-    const double* colB[MAXG];          // product only: column factor T1[ev] of row bit b
-    const double* dA;                  // pair: A part of the diagonal; product: the full diagonal vector
-    const double* dB;                  // pair: B part of the diagonal
-    int KC, KR;
-};
-
-__device__ __forceinline__ bool tiled_space(const SpaceDev& sp)
-{
-    if ((int)sp.KA + (int)sp.KB < BIGK || sp.kind == K_PRE) return false;
-    if (sp.kind == K_JOINT) return !sp.splitA && !sp.splitB && sp.KA >= 4;
-    return sp.splitA >= 4;
-}
-
-__device__ __forceinline__ void tile_ctx_build(TileCtx& c, const SpaceDev& sp, const double* __restrict__ S, int t)
-{
-    if (sp.kind == K_JOINT) {
-        const int KA = sp.KA, KB = sp.KB;
-        if (t < KA) { c.colA[t] = S + sp.tabA + ((uint64_t)sp.evA[t] << KA); c.rowA[t] = &c_one; }
-        if (t < KB) { c.rowB[t] = S + sp.tabB + ((uint64_t)sp.evB[t] << KB); c.colB[t] = &c_one; }
-        if (t == 0) {
-            c.dA = S + sp.tabA + ((uint64_t)ROW_D << KA);
-            c.dB = S + sp.tabB + ((uint64_t)ROW_D << KB);
-            c.KC = KA; c.KR = KB;
-        }
-    } else {
-        const int K1 = sp.splitA, K2 = sp.KA - K1;
-        const double* T1 = S + sp.tabA;
-        const double* T2 = T1 + ((uint64_t)NR << K1);
-        if (t < K1) { c.colA[t] = T1 + ((uint64_t)sp.evA[t] << K1); c.rowA[t] = T2 + ((uint64_t)sp.evA[t] << K2); }
-        if (t < K2) { c.rowB[t] = T2 + ((uint64_t)sp.evA[K1 + t] << K2); c.colB[t] = T1 + ((uint64_t)sp.evA[K1 + t] << K1); }
-        if (t == 0) { c.dA = T2 + ((uint64_t)NR << K2); c.dB = &c_zero; c.KC = K1; c.KR = K2; }
-    }
-}
-
 // 32-byte global load / store (LDG.E.256 / STG.E.256 on sm_100a): four lanes cover one 128-byte line with a single
 // request, which halves the L1 wavefronts of the tile kernels against two 16-byte loads per lane.
 __device__ __forceinline__ void ld4(const double* __restrict__ p, double (&f)[4])
@@ -756,945 +695,126 @@ __device__ __forceinline__ void st4(double* __restrict__ p, double a, double b, 
     asm volatile("st.global.v4.f64 [%4], {%0,%1,%2,%3};" :: "d"(a), "d"(b), "d"(c), "d"(d), "l"(p) : "memory");
 }
 
-// right-hand side of the four states of a lane: non-zero on few states only (except the second phase's start vector)
-template <bool ADJ>
-__device__ __forceinline__ void tile_rhs(const SpaceDev& sp, const SpaceDev* __restrict__ spaces, const double* __restrict__ S,
-                                         int KC, int KR, uint32_t row, uint32_t lo0, double (&acc)[4])
+// ------------------------------------------------------------------------------------------
+// Big tier (K >= BIGK): blocked substitution, one warp per 2^12-state block kept in shared memory, launches level by
+// level over the popcount of the K-12 outer bits (mmh_blk.cuh has the algorithm; this is the adapter from a space's
+// tables to its abstract description and the kernel around it).
+//   pair (no split tables, KA >= 3 or KA == 0): an A-bit's rate is the vector T_A[ev][uA], a B-bit's rate the scalar
+//       T_B[ev][uB]; diag = D_A[uA] + D_B[uB]
+//   single-tumour space in product form with K1 = 8: rate = T1[ev][u & 255] * T2[ev][u >> 8], full diagonal vector
+constexpr int BLKW = 6;                                  // warps (= blocks in flight) per CTA: 6 x 32 KB of shared memory
+
+__host__ __device__ __forceinline__ bool blocked_space(const SpaceDev& sp)
 {
-    const uint32_t s0 = (row << KC) | lo0;
+    const int K = (int)sp.KA + (int)sp.KB;
+    if (K < BIGK || sp.kind == K_PRE) return false;
+    if (sp.kind == K_JOINT) return !sp.splitA && !sp.splitB && (sp.KA >= 3 || sp.KA == 0);
+    return sp.splitA == BLK_CB;
+}
+
+__device__ __forceinline__ void blk_ctx_build(BlkCtx& c, const SpaceDev& sp, const double* __restrict__ S, int tid)
+{
+    const int KA = sp.KA, KB = sp.KB, K = KA + KB;
+    const bool joint = sp.kind == K_JOINT;
+    if (tid < K) {
+        BlkBit b;
+        b.pad = 0;
+        if (joint) {
+            if (tid < KA) { b.P = S + sp.tabA + ((uint64_t)sp.evA[tid] << KA); b.mP = (1u << KA) - 1u; b.Q = nullptr; b.mQ = 0; b.shQ = 3; }
+            else if (KA == 0) { b.P = S + sp.tabB + ((uint64_t)sp.evB[tid] << KB); b.mP = (1u << KB) - 1u; b.Q = nullptr; b.mQ = 0; b.shQ = 3; }
+            else { b.P = nullptr; b.mP = 7u; b.Q = S + sp.tabB + ((uint64_t)sp.evB[tid - KA] << KB); b.mQ = (1u << KB) - 1u; b.shQ = (uint32_t)KA; }
+        } else {
+            const int K2 = K - BLK_CB;
+            const double* T1 = S + sp.tabA;
+            const double* T2 = T1 + ((uint64_t)NR << BLK_CB);
+            b.P = T1 + ((uint64_t)sp.evA[tid] << BLK_CB); b.mP = (1u << BLK_CB) - 1u;
+            b.Q = T2 + ((uint64_t)sp.evA[tid] << K2); b.mQ = (1u << K2) - 1u; b.shQ = BLK_CB;
+        }
+        c.bit[tid] = b;
+    }
+    if (tid == 0) {
+        if (joint) {
+            const double* dA = S + sp.tabA + ((uint64_t)ROW_D << KA);
+            const double* dB = S + sp.tabB + ((uint64_t)ROW_D << KB);
+            if (KA == 0) { c.d1 = dB; c.m1 = (1u << KB) - 1u; c.d2 = dA; c.m2 = 0; c.sh2 = 0; }
+            else { c.d1 = dA; c.m1 = (1u << KA) - 1u; c.d2 = dB; c.m2 = (1u << KB) - 1u; c.sh2 = (uint32_t)KA; }
+        } else {
+            const int K2 = K - BLK_CB;
+            c.d1 = S + sp.tabA + ((uint64_t)NR << BLK_CB) + ((uint64_t)NR << K2);
+            c.m1 = (1u << K) - 1u; c.d2 = nullptr; c.m2 = 0; c.sh2 = 0;
+        }
+        blk_ctx_layout(c, K, (joint && KA > BLK_CB) ? KA : BLK_CB);
+    }
+    __syncthreads();
+    if (tid < BLK_Q) blk_ctx_cs_row(c, tid);
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t dep = 0;
+        for (int q = 0; q < BLK_Q; ++q)
+            for (int t = 0; t < BLK_CB; ++t) if (c.cs[q][t] != 1.0) dep |= 1u << t;
+        c.seqdep = dep;
+    }
+    __syncthreads();
+}
+
+// right-hand side of the eight states of a lane: non-zero on few chunks only (except the second phase's start vector)
+template <bool ADJ>
+struct BlkRhs {
+    const SpaceDev& sp;
+    const SpaceDev* __restrict__ spaces;
+    const double* __restrict__ S;
+    __device__ __forceinline__ void operator()(uint32_t s0, double (&acc)[8]) const
     {
-        const uint32_t NC = 1u << KC, NRW = 1u << KR;
+        const int KA = sp.KA, KB = sp.KB;
+        const uint32_t NA = 1u << KA, NB = 1u << KB;
+        const uint32_t lo0 = s0 & (NA - 1u), row = s0 >> KA;         // pair, KA >= 3: the chunk lies in one row
         bool any;
         if (!ADJ) {
-            if (sp.kind == K_JOINT) any = row < (1u << sp.nb) && ((row ^ lo0) & ~3u) == 0u;
+            if (sp.kind == K_JOINT) any = KA == 0 ? s0 == 0u : (row < (1u << sp.nb) && ((row ^ lo0) & ~7u) == 0u);
             else if (sp.kind == K_PF || sp.kind == K_MF) any = true;
             else any = s0 == 0u;
         } else {
-            if (sp.kind == K_JOINT) any = (sp.has_pf && (lo0 | 3u) == NC - 1u) || (sp.has_mf && row == NRW - 1u);
-            else any = (s0 | 3u) == (NC << KR) - 1u;
+            if (sp.kind == K_JOINT) any = KA == 0 ? true : ((sp.has_pf && (lo0 | 7u) == NA - 1u) || (sp.has_mf && row == NB - 1u));
+            else any = (s0 | 7u) == (NA << KB) - 1u;
         }
         if (any) {
 #pragma unroll
-            for (int t = 0; t < 4; ++t) acc[t] = ADJ ? rhs_adj(sp, spaces, S, s0 + t) : rhs_fwd(sp, spaces, S, s0 + t);
+            for (int t = 0; t < 8; ++t) acc[t] = ADJ ? rhs_adj(sp, spaces, S, s0 + t) : rhs_fwd(sp, spaces, S, s0 + t);
         }
     }
-}
+};
 
-// edges on the row bits of a lane's four states (sources in global memory): acc += rate * v[other row]
-template <bool ADJ, bool PROD>
-__device__ __forceinline__ void tile_row_edges(const TileCtx& c, const double* __restrict__ v, uint32_t row, uint32_t lo0,
-                                               double (&acc)[4])
-{
-    const int KC = c.KC, KR = c.KR;
-    {
-        constexpr int NB = TILE_NBB;
-        uint32_t m = ADJ ? (~row & ((1u << KR) - 1u)) : row;
-        while (m) {
-            double y[NB][4], k[NB];
-            int bq[NB];
-#pragma unroll
-            for (int q = 0; q < NB; ++q) {
-                const bool on = m != 0u;
-                const int b = on ? __ffs(m) - 1 : 0;
-                m &= m - 1;
-                bq[q] = b;
-                const uint32_t orow = row ^ (1u << b);
-                if (on) {
-                    k[q] = c.rowB[b][ADJ ? row : orow];
-                    ld4(v + (((uint64_t)orow << KC) | lo0), y[q]);
-                } else {
-                    k[q] = 0.0;
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) y[q][t] = 0.0;
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < NB; ++q) {
-                if (PROD) {
-                    double cf[4];
-                    ld4(c.colB[bq[q]] + lo0, cf);
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) acc[t] = fma(cf[t] * k[q], y[q][t], acc[t]);
-                } else {
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) acc[t] = fma(k[q], y[q][t], acc[t]);
-                }
-            }
-        }
-    }
-}
-
-// diagonal, column bits 0,1 (inside the lane) and 2,3 (across the four lanes of a row group): acc -> val
-template <bool ADJ, bool PROD>
-__device__ __forceinline__ void tile_tail(const TileCtx& c, uint32_t row, uint32_t lo0, int lane, double (&acc)[4], double (&val)[4])
-{
-    const int KC = c.KC;
-    const int lc = lane & 3;
-    const uint32_t s0 = (row << KC) | lo0;
-    // ---- diagonal ----
-    double inv[4];
-    {
-        double d[4];
-        if (PROD) ld4(c.dA + s0, d);
-        else {
-            ld4(c.dA + lo0, d);
-            const double k = c.dB[row];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) d[t] += k;
-        }
-#pragma unroll
-        for (int t = 0; t < 4; ++t) inv[t] = 1.0 / d[t];
-    }
-    // ---- column bits 0,1 (inside the lane) and 2,3 (across the four lanes of the row group) ----
-    double k0 = 1.0, k1 = 1.0, k2 = 1.0, k3 = 1.0;
-    if (PROD) { k0 = c.rowA[0][row]; k1 = c.rowA[1][row]; k2 = c.rowA[2][row]; k3 = c.rowA[3][row]; }
-    double e0a, e0b, e1a, e1b;
-    {
-        double q0[4], q1[4];
-        ld4(c.colA[0] + lo0, q0);
-        ld4(c.colA[1] + lo0, q1);
-        e0a = q0[0] * k0; e0b = q0[2] * k0;          // bit 0: 0 -> 1, 2 -> 3
-        e1a = q1[0] * k1; e1b = q1[1] * k1;          // bit 1: 0 -> 2, 1 -> 3
-    }
-    double w0[4] = {0.0, 0.0, 0.0, 0.0}, w1a[4] = {0.0, 0.0, 0.0, 0.0}, w1b[4] = {0.0, 0.0, 0.0, 0.0};
-    const int pl = __popc(lc);
-    if (!ADJ) {
-        // round 0: lanes 1, 2 receive from lane 0;  round 1: lane 3 receives from lanes 2 (bit 2) and 1 (bit 3)
-        if (pl == 1) {
-            const int q = lc == 2;
-            ld4(c.colA[2 + q] + (lo0 ^ (4u << q)), w0);
-            const double k = q ? k3 : k2;
-#pragma unroll
-            for (int t = 0; t < 4; ++t) w0[t] *= k;
-        } else if (lc == 3) {
-            ld4(c.colA[2] + (lo0 ^ 4u), w1a);
-            ld4(c.colA[3] + (lo0 ^ 8u), w1b);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) { w1a[t] *= k2; w1b[t] *= k3; }
-        }
-    } else {
-        // round 0: lanes 1, 2 receive from lane 3;  round 1: lane 0 receives from lanes 1 (bit 2) and 2 (bit 3)
-        if (pl == 1) {
-            const int q = lc == 1;                   // the bit this lane lacks
-            ld4(c.colA[2 + q] + lo0, w0);
-            const double k = q ? k3 : k2;
-#pragma unroll
-            for (int t = 0; t < 4; ++t) w0[t] *= k;
-        } else if (lc == 0) {
-            ld4(c.colA[2] + lo0, w1a);
-            ld4(c.colA[3] + lo0, w1b);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) { w1a[t] *= k2; w1b[t] *= k3; }
-        }
-    }
-    auto fin = [&]() {
-        if (!ADJ) {
-            val[0] = acc[0] * inv[0];
-            val[1] = fma(e0a, val[0], acc[1]) * inv[1];
-            val[2] = fma(e1a, val[0], acc[2]) * inv[2];
-            val[3] = fma(e0b, val[2], fma(e1b, val[1], acc[3])) * inv[3];
-        } else {
-            val[3] = acc[3] * inv[3];
-            val[2] = fma(e0b, val[3], acc[2]) * inv[2];
-            val[1] = fma(e1b, val[3], acc[1]) * inv[1];
-            val[0] = fma(e0a, val[1], fma(e1a, val[2], acc[0])) * inv[0];
-        }
-    };
-    // Values of lanes that are not final yet are finite partial results and only ever meet a zero weight.
-    fin();
-    {
-        const int src = ADJ ? (lane | 3) : (lane & ~3);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) acc[t] = fma(w0[t], __shfl_sync(0xffffffffu, val[t], src), acc[t]);
-    }
-    fin();
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        const double p = __shfl_xor_sync(0xffffffffu, val[t], 1);
-        const double q = __shfl_xor_sync(0xffffffffu, val[t], 2);
-        acc[t] = fma(w1b[t], q, fma(w1a[t], p, acc[t]));
-    }
-    fin();
-}
-
-template <bool ADJ, bool PROD>
-__device__ __forceinline__ void solve_tile16(const SpaceDev& sp, const SpaceDev* __restrict__ spaces, const TileCtx& c,
-                                             double* __restrict__ S, uint32_t cA, uint32_t row, bool valid, int lane)
-{
-    const int KC = c.KC, KR = c.KR;
-    const int lc = lane & 3;
-    const uint32_t lo0 = (cA << 4) | ((uint32_t)lc << 2);
-    const uint32_t s0 = (row << KC) | lo0;
-    double* v = S + (ADJ ? sp.x_off : sp.y_off);
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    tile_rhs<ADJ>(sp, spaces, S, KC, KR, row, lo0, acc);
-    // Edges are taken NB at a time, all loads of a round before its FMAs: a tile is a chain of dependent rounds and
-    // thin levels have no other warps to hide the memory latency behind.
-    // ---- column bits >= 4 (uniform over the warp): FWD visits the set bits of cA, ADJ the unset ones ----
-    {
-        constexpr int NB = TILE_NBA;
-        uint32_t m = ADJ ? (~cA & ((1u << (KC - 4)) - 1u)) : cA;
-        while (m) {
-            double r[NB][4], y[NB][4], k[NB];
-#pragma unroll
-            for (int q = 0; q < NB; ++q) {
-                const bool on = m != 0u;
-                const int a = on ? __ffs(m) + 3 : 4;
-                m &= m - 1;
-                const uint32_t bit = 1u << a;
-                k[q] = 1.0;
-                if (on) {
-                    ld4(c.colA[a] + (ADJ ? lo0 : (lo0 ^ bit)), r[q]);
-                    ld4(v + (s0 ^ bit), y[q]);
-                    if (PROD) k[q] = c.rowA[a][row];
-                } else {
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) { r[q][t] = 0.0; y[q][t] = 0.0; }
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < NB; ++q)
-#pragma unroll
-                for (int t = 0; t < 4; ++t) acc[t] = fma(PROD ? r[q][t] * k[q] : r[q][t], y[q][t], acc[t]);
-        }
-    }
-    tile_row_edges<ADJ, PROD>(c, v, row, lo0, acc);
-    double val[4];
-    tile_tail<ADJ, PROD>(c, row, lo0, lane, acc, val);
-    if (valid) st4(v + s0, val[0], val[1], val[2], val[3]);
-}
-
-// item: space, a = lA | lB << 8 | tiles << 16, b = first tile; tile t -> column block t / nBg, row group t % nBg
+// item: space, a = outer level, b = first block of that level (index into the popcount-sorted list), c = blocks
 template <bool ADJ>
-__global__ void __launch_bounds__(256, TILE_CTAS)
-k_solve_tile(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs, const uint32_t* __restrict__ hs,
-             const uint32_t* __restrict__ hsidx, double* __restrict__ S)
+__global__ void __launch_bounds__(BLKW * 32, 1)
+k_blk(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, const uint32_t* __restrict__ hs,
+      const uint32_t* __restrict__ hsidx, double* __restrict__ S)
 {
-    __shared__ TileCtx ctx;
-    const Item sg = segs[blockIdx.x];
-    const SpaceDev& sp = spaces[sg.space];
-    tile_ctx_build(ctx, sp, S, threadIdx.x);
-    __syncthreads();
+    extern __shared__ __align__(16) double blk_sm[];
+    __shared__ BlkCtx ctx;
+    const Item it = items[blockIdx.x];
+    const SpaceDev& sp = spaces[it.space];
+    blk_ctx_build(ctx, sp, S, threadIdx.x);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint32_t lA = sg.a & 255u, lB = (sg.a >> 8) & 255u, cnt = sg.a >> 16;
-    const uint32_t offA = hsidx[(ctx.KC - 4) * 32 + lA];
-    const uint32_t offB = hsidx[ctx.KR * 32 + lB];
-    const uint32_t nB = hsidx[ctx.KR * 32 + lB + 1] - offB;
-    const uint32_t nBg = (nB + 7u) >> 3;
-    const bool prod = sp.kind != K_JOINT;
-    for (uint32_t q = w; q < cnt; q += 8) {
-        const uint32_t t = sg.b + q;
-        const uint32_t iA = t / nBg, jB = t - iA * nBg;
-        const uint32_t ri = jB * 8u + (uint32_t)(lane >> 2);
-        const bool valid = ri < nB;
-        const uint32_t cA = hs[offA + iA];
-        const uint32_t row = hs[offB + min(ri, nB - 1u)];
-        if (prod) solve_tile16<ADJ, true>(sp, spaces, ctx, S, cA, row, valid, lane);
-        else      solve_tile16<ADJ, false>(sp, spaces, ctx, S, cA, row, valid, lane);
-    }
-}
-
-// Experimental SM-local scheduling of the tile solve (MMH_SMLOCAL=1, fat levels only).  Every source line of a
-// row edge is read by the ~KR/2 successor rows of the same column block; launched as independent CTAs those readers
-// are scattered over the SMs and every read goes to L2 (76 B of L2 traffic per state).  Here the items of a launch
-// are split into windows of SM_WIN consecutive items (about one column block with all its rows of the level);
-// window j belongs to the queue of SM j % nsm, a persistent CTA pulls items from the queue of the SM it runs on
-// (%smid), so that the readers of a line share one L1.  When its queue is empty a CTA helps with whatever queue still
-// has items (needed for correctness too: an SM may host no CTA of this launch).  Results do not depend on which CTA
-// runs an item.
-constexpr uint32_t SM_WIN = 4;
-
-__device__ __forceinline__ uint32_t smq_len(uint32_t q, uint32_t n_items, uint32_t nsm)
-{
-    // items of queue q: windows q, q + nsm, ... each SM_WIN items, the last one possibly cut by n_items
-    const uint32_t nwin = (n_items + SM_WIN - 1) / SM_WIN;
-    if (q >= nwin) return 0;
-    const uint32_t mine = (nwin - 1 - q) / nsm + 1;              // windows of this queue
-    const uint32_t last = q + (mine - 1) * nsm;                  // its last window
-    const uint32_t in_last = min(SM_WIN, n_items - last * SM_WIN);
-    return (mine - 1) * SM_WIN + in_last;
-}
-
-template <bool ADJ>
-__global__ void __launch_bounds__(256, TILE_CTAS)
-k_solve_tile_sm(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs, uint32_t n_items,
-                const uint32_t* __restrict__ hs, const uint32_t* __restrict__ hsidx, double* __restrict__ S,
-                uint32_t* __restrict__ ctr, uint32_t nsm)
-{
-    __shared__ TileCtx ctx;
-    __shared__ uint32_t s_item, s_queue;
-    uint32_t smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    uint32_t queue = smid % nsm, cur_space = 0xffffffffu;
-    for (;;) {
-        // ---- next item of the current queue ----
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t id = 0xffffffffu;
-            if (queue != 0xffffffffu) {
-                const uint32_t k = atomicAdd(&ctr[queue], 1u);
-                if (k < smq_len(queue, n_items, nsm)) id = (queue + nsm * (k / SM_WIN)) * SM_WIN + (k % SM_WIN);
-            }
-            s_item = id;
-        }
-        __syncthreads();
-        uint32_t id = s_item;
-        if (id == 0xffffffffu) {
-            // ---- queue empty: look for any queue that still has items ----
-            if (threadIdx.x == 0) s_queue = 0xffffffffu;
-            __syncthreads();
-            for (uint32_t q = threadIdx.x; q < nsm; q += blockDim.x)
-                if (*reinterpret_cast<volatile uint32_t*>(ctr + q) < smq_len(q, n_items, nsm)) atomicMin(&s_queue, q);
-            __syncthreads();
-            queue = s_queue;
-            if (queue == 0xffffffffu) return;                    // every queue is drained (uniform over the CTA)
-            continue;
-        }
-        const Item sg = segs[id];
-        const SpaceDev& sp = spaces[sg.space];
-        if (sg.space != cur_space) {
-            tile_ctx_build(ctx, sp, S, threadIdx.x);
-            cur_space = sg.space;
-            __syncthreads();
-        }
-        const uint32_t lA = sg.a & 255u, lB = (sg.a >> 8) & 255u, cnt = sg.a >> 16;
-        const uint32_t offA = hsidx[(ctx.KC - 4) * 32 + lA];
-        const uint32_t offB = hsidx[ctx.KR * 32 + lB];
-        const uint32_t nB = hsidx[ctx.KR * 32 + lB + 1] - offB;
-        const uint32_t nBg = (nB + 7u) >> 3;
-        const bool prod = sp.kind != K_JOINT;
-        for (uint32_t q = w; q < cnt; q += 8) {
-            const uint32_t t = sg.b + q;
-            const uint32_t iA = t / nBg, jB = t - iA * nBg;
-            const uint32_t ri = jB * 8u + (uint32_t)(lane >> 2);
-            const bool valid = ri < nB;
-            const uint32_t cA = hs[offA + iA];
-            const uint32_t row = hs[offB + min(ri, nB - 1u)];
-            if (prod) solve_tile16<ADJ, true>(sp, spaces, ctx, S, cA, row, valid, lane);
-            else      solve_tile16<ADJ, false>(sp, spaces, ctx, S, cA, row, valid, lane);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// Two-dimensional blocked forward solve of a pair (experimental, MMH_BLOCK=1).  A CTA owns the
-// sub-lattice spanned by the d_r LOWEST row bits and the d_c LOWEST column-block bits (plus the 4 in-tile column
-// bits): 2^(d_r + d_c + 4) <= BLK_STATES states held in shared memory, i.e. rows rH 2^d_r + rl (rl < 2^d_r) and the
-// 2^(d_c + 4) consecutive columns of column blocks cH 2^d_c + cl.  Launch levels run over popcount(cH) + popcount(rH)
-// only.  Phase 1 adds, for every 16-state tile (rl, cl) of the block, the right-hand side and the edges on the bits of
-// cH and rH (sources are blocks finished by earlier launches; uniform trip counts over the whole CTA).  Phase 2 walks the
-// d + 1 inner levels of the combined index m = rl << d_c | cl (popcount-sorted list of d-bit numbers) with
-// __syncthreads in between: edges on inside bits read shared memory, bits 0..3 are resolved by tile_tail.  The 128-byte
-// line reads per state drop from (K - 4) / 2 to (K - 4 - d) / 2.
-constexpr int BLK_STATES = 4096;
-constexpr int BLK_D = 8;                             // inside bits (rows + column blocks)
-
-__host__ __device__ inline void block_dims(int KA, int KB, int& d_c, int& d_r)
-{
-    d_c = KA - 4 < 4 ? KA - 4 : 4;
-    d_r = KB < BLK_D - d_c ? KB : BLK_D - d_c;
-    if (d_c + d_r < BLK_D) d_c = KA - 4 < BLK_D - d_r ? KA - 4 : BLK_D - d_r;
-}
-
-// item: a = lA' | lB' << 8 (popcounts of the outside column-block / row bits), b = block index inside the split
-__global__ void __launch_bounds__(256, 3)
-k_solve_block_fwd(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs, const uint32_t* __restrict__ hs,
-                  const uint32_t* __restrict__ hsidx, double* __restrict__ S)
-{
-    extern __shared__ double Yt[];                    // [rl][cl * 16 + column], row stride 2^(d_c + 4)
-    __shared__ TileCtx ctx;
-    const Item sg = segs[blockIdx.x];
-    const SpaceDev& sp = spaces[sg.space];
-    tile_ctx_build(ctx, sp, S, threadIdx.x);
-    __syncthreads();
-    const TileCtx& c = ctx;
-    const int KC = c.KC, KR = c.KR;
-    int d_c, d_r;
-    block_dims(KC, KR, d_c, d_r);
-    const int d = d_c + d_r, kbA = KC - 4 - d_c, kbB = KR - d_r;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, lc = lane & 3, lg = lane >> 2;
-    const uint32_t lA = sg.a & 255u, lB = (sg.a >> 8) & 255u;
-    const uint32_t offA = hsidx[kbA * 32 + lA];
-    const uint32_t offB = hsidx[kbB * 32 + lB], nBo = hsidx[kbB * 32 + lB + 1] - offB;
-    const uint32_t iA = sg.b / nBo, iB = sg.b - iA * nBo;
-    const uint32_t cH = hs[offA + iA], rH = hs[offB + iB];
-    const uint32_t rs = 1u << (d_c + 4);              // row stride of the shared block
-    const uint32_t ntile = 1u << d;
-    double* v = S + sp.y_off;
-    // ---- phase 1: right-hand side and edges on the outside bits, tiles in natural order ----
-    for (uint32_t m0 = (uint32_t)w * 8u; m0 < ntile; m0 += 64u) {
-        const uint32_t m = min(m0 + (uint32_t)lg, ntile - 1u);
-        const bool valid = m0 + (uint32_t)lg < ntile;
-        const uint32_t rl = m >> d_c, cl = m & ((1u << d_c) - 1u);
-        const uint32_t row = (rH << d_r) | rl;
-        const uint32_t cA = (cH << d_c) | cl;
-        const uint32_t lo0 = (cA << 4) | ((uint32_t)lc << 2);
-        const uint32_t s0 = (row << KC) | lo0;
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        tile_rhs<false>(sp, spaces, S, KC, KR, row, lo0, acc);
-        {
-            constexpr int NB = TILE_NBA;
-            uint32_t mm = cH;                            // outside column-block bits: uniform over the CTA
-            while (mm) {
-                double r[NB][4], y[NB][4];
-#pragma unroll
-                for (int e = 0; e < NB; ++e) {
-                    const bool on = mm != 0u;
-                    const int a = on ? __ffs(mm) + 3 + d_c : 4;
-                    mm &= mm - 1;
-                    const uint32_t bit = 1u << a;
-                    if (on) { ld4(c.colA[a] + (lo0 ^ bit), r[e]); ld4(v + (s0 ^ bit), y[e]); }
-                    else {
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) { r[e][t] = 0.0; y[e][t] = 0.0; }
-                    }
-                }
-#pragma unroll
-                for (int e = 0; e < NB; ++e)
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) acc[t] = fma(r[e][t], y[e][t], acc[t]);
-            }
-        }
-        {
-            constexpr int NB = TILE_NBB;
-            uint32_t mm = rH;                            // outside row bits: uniform over the CTA
-            while (mm) {
-                double y[NB][4], k[NB];
-#pragma unroll
-                for (int e = 0; e < NB; ++e) {
-                    const bool on = mm != 0u;
-                    const int b = on ? __ffs(mm) - 1 + d_r : 0;
-                    mm &= mm - 1;
-                    const uint32_t orow = row ^ (1u << b);
-                    if (on) { k[e] = c.rowB[b][orow]; ld4(v + (((uint64_t)orow << KC) | lo0), y[e]); }
-                    else {
-                        k[e] = 0.0;
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) y[e][t] = 0.0;
-                    }
-                }
-#pragma unroll
-                for (int e = 0; e < NB; ++e)
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) acc[t] = fma(k[e], y[e][t], acc[t]);
-            }
-        }
-        if (valid) {
-            double2* o = reinterpret_cast<double2*>(Yt + rl * rs + (cl << 4) + ((uint32_t)lc << 2));
-            o[0] = make_double2(acc[0], acc[1]);
-            o[1] = make_double2(acc[2], acc[3]);
-        }
-    }
-    __syncthreads();
-    // ---- phase 2: inner levels of the combined index m (popcount j), edges on inside bits from shared memory ----
-    for (int j = 0; j <= d; ++j) {
-        const uint32_t offD = hsidx[d * 32 + j];
-        const uint32_t units = hsidx[d * 32 + j + 1] - offD;
-        for (uint32_t u0 = (uint32_t)w * 8u; u0 < units; u0 += 64u) {
-            const bool valid = u0 + (uint32_t)lg < units;
-            const uint32_t m = hs[offD + min(u0 + (uint32_t)lg, units - 1u)];
-            const uint32_t rl = m >> d_c, cl = m & ((1u << d_c) - 1u);
-            const uint32_t row = (rH << d_r) | rl;
-            const uint32_t cA = (cH << d_c) | cl;
-            const uint32_t lo0 = (cA << 4) | ((uint32_t)lc << 2);
-            const uint32_t so = rl * rs + (cl << 4) + ((uint32_t)lc << 2);      // own tile in the shared block
-            double acc[4];
-            {
-                const double2* a2 = reinterpret_cast<const double2*>(Yt + so);
-                const double2 p0 = a2[0], p1 = a2[1];
-                acc[0] = p0.x; acc[1] = p0.y; acc[2] = p1.x; acc[3] = p1.y;
-            }
-            uint32_t mm = m;                             // inside bits: popcount j in every lane group
-            while (mm) {
-                const int p = __ffs(mm) - 1;
-                mm &= mm - 1;
-                double y[4];
-                if (p < d_c) {                           // column-block bit: source tile (rl, cl - bit), rate vector of the source columns
-                    const double2* y2 = reinterpret_cast<const double2*>(Yt + (so ^ (16u << p)));
-                    const double2 p0 = y2[0], p1 = y2[1];
-                    y[0] = p0.x; y[1] = p0.y; y[2] = p1.x; y[3] = p1.y;
-                    double r[4];
-                    ld4(c.colA[4 + p] + (lo0 ^ (16u << p)), r);
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) acc[t] = fma(r[t], y[t], acc[t]);
-                } else {                                 // row bit: source tile (rl - bit, cl), one scalar rate
-                    const int b = p - d_c;
-                    const double2* y2 = reinterpret_cast<const double2*>(Yt + (so - (rs << b)));
-                    const double2 p0 = y2[0], p1 = y2[1];
-                    y[0] = p0.x; y[1] = p0.y; y[2] = p1.x; y[3] = p1.y;
-                    const double k = c.rowB[b][row ^ (1u << b)];
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) acc[t] = fma(k, y[t], acc[t]);
-                }
-            }
-            double val[4];
-            tile_tail<false, false>(c, row, lo0, lane, acc, val);
-            if (valid) {
-                double2* o = reinterpret_cast<double2*>(Yt + so);
-                o[0] = make_double2(val[0], val[1]);
-                o[1] = make_double2(val[2], val[3]);
-                st4(v + (((uint64_t)row << KC) | lo0), val[0], val[1], val[2], val[3]);
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// Second version of the blocked forward solve (MMH_BLOCK=2).  NOT YET RUN ON A GPU (written after the round's GPU
-// budget was spent; version 1 above is tested).  Version 1 measured slower than the tile kernel (forward solve 90 ->
-// 109 ms serial) although it halves the line reads: its phase 2 fetches the rate vectors of every inner-level tile
-// from global memory (two dependent latencies per round, ten rounds per block).  Here everything phase 2 needs is
-// staged in shared memory once per block: the rate rows of the 4 + d_c inside column bits and the diagonal part dA
-// over the block's columns, the diagonal part dB and the inside row-bit rates over the block's rows.
-//   shared layout (doubles): Yt[BLK_STATES] | Rc[(4 + d_c)][rs] | dAc[rs] | dBr[nr] | Rr[d_r][nr]   (rs = 2^(d_c+4), nr = 2^d_r)
-constexpr int BLK2_SMEM_DOUBLES = BLK_STATES + 8 * 256 + 256 + 256 + 8 * 256;
-
-__device__ __forceinline__ void tile_tail_fwd_s(const double* __restrict__ Rc, uint32_t rs, const double* __restrict__ dAc,
-                                                double dBv, uint32_t lcol, int lane, double (&acc)[4], double (&val)[4])
-{
-    const int lc = lane & 3;
-    double inv[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) inv[t] = 1.0 / (dAc[lcol + t] + dBv);
-    const double e0a = Rc[lcol], e0b = Rc[lcol + 2];                       // bit 0: 0 -> 1, 2 -> 3
-    const double e1a = Rc[rs + lcol], e1b = Rc[rs + lcol + 1];              // bit 1: 0 -> 2, 1 -> 3
-    double w0[4] = {0.0, 0.0, 0.0, 0.0}, w1a[4] = {0.0, 0.0, 0.0, 0.0}, w1b[4] = {0.0, 0.0, 0.0, 0.0};
-    const int pl = __popc(lc);
-    if (pl == 1) {
-        const int q = lc == 2;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) w0[t] = Rc[(2 + q) * rs + (lcol ^ (4u << q)) + t];
-    } else if (lc == 3) {
-#pragma unroll
-        for (int t = 0; t < 4; ++t) { w1a[t] = Rc[2 * rs + (lcol ^ 4u) + t]; w1b[t] = Rc[3 * rs + (lcol ^ 8u) + t]; }
-    }
-    auto fin = [&]() {
-        val[0] = acc[0] * inv[0];
-        val[1] = fma(e0a, val[0], acc[1]) * inv[1];
-        val[2] = fma(e1a, val[0], acc[2]) * inv[2];
-        val[3] = fma(e0b, val[2], fma(e1b, val[1], acc[3])) * inv[3];
-    };
-    fin();
-#pragma unroll
-    for (int t = 0; t < 4; ++t) acc[t] = fma(w0[t], __shfl_sync(0xffffffffu, val[t], lane & ~3), acc[t]);
-    fin();
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        const double p = __shfl_xor_sync(0xffffffffu, val[t], 1);
-        const double q = __shfl_xor_sync(0xffffffffu, val[t], 2);
-        acc[t] = fma(w1b[t], q, fma(w1a[t], p, acc[t]));
-    }
-    fin();
-}
-
-__global__ void __launch_bounds__(256, 3)
-k_solve_block_fwd2(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs, const uint32_t* __restrict__ hs,
-                   const uint32_t* __restrict__ hsidx, double* __restrict__ S)
-{
-    extern __shared__ double smem2[];
-    __shared__ TileCtx ctx;
-    const Item sg = segs[blockIdx.x];
-    const SpaceDev& sp = spaces[sg.space];
-    tile_ctx_build(ctx, sp, S, threadIdx.x);
-    __syncthreads();
-    const TileCtx& c = ctx;
-    const int KC = c.KC, KR = c.KR;
-    int d_c, d_r;
-    block_dims(KC, KR, d_c, d_r);
-    const int d = d_c + d_r, kbA = KC - 4 - d_c, kbB = KR - d_r;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, lc = lane & 3, lg = lane >> 2;
-    const uint32_t lA = sg.a & 255u, lB = (sg.a >> 8) & 255u;
-    const uint32_t offA = hsidx[kbA * 32 + lA];
-    const uint32_t offB = hsidx[kbB * 32 + lB], nBo = hsidx[kbB * 32 + lB + 1] - offB;
-    const uint32_t iA = sg.b / nBo, iB = sg.b - iA * nBo;
-    const uint32_t cH = hs[offA + iA], rH = hs[offB + iB];
-    const uint32_t rs = 1u << (d_c + 4), nr = 1u << d_r;
-    const uint32_t ntile = 1u << d;
-    const uint32_t colbase = cH << (d_c + 4), rowbase = rH << d_r;
-    double* Yt = smem2;
-    double* Rc = Yt + BLK_STATES;
-    double* dAc = Rc + (size_t)(4 + d_c) * rs;
-    double* dBr = dAc + rs;
-    double* Rr = dBr + nr;
-    double* v = S + sp.y_off;
-    // ---- phase 0: stage the block's rates and diagonal parts ----
-    for (uint32_t i = threadIdx.x; i < (uint32_t)(4 + d_c) * rs; i += blockDim.x) {
-        const uint32_t q = i / rs, jcol = i - q * rs;
-        Rc[i] = c.colA[q][colbase + jcol];
-    }
-    for (uint32_t i = threadIdx.x; i < rs; i += blockDim.x) dAc[i] = c.dA[colbase + i];
-    for (uint32_t i = threadIdx.x; i < nr; i += blockDim.x) dBr[i] = c.dB[rowbase + i];
-    for (uint32_t i = threadIdx.x; i < (uint32_t)d_r * nr; i += blockDim.x) {
-        const uint32_t b = i / nr, rl = i - b * nr;
-        Rr[i] = c.rowB[b][rowbase + rl];                  // rate of adding row bit b at (source) row rl
-    }
-    // ---- phase 1: as in version 1 ----
-    for (uint32_t m0 = (uint32_t)w * 8u; m0 < ntile; m0 += 64u) {
-        const uint32_t m = min(m0 + (uint32_t)lg, ntile - 1u);
-        const bool valid = m0 + (uint32_t)lg < ntile;
-        const uint32_t rl = m >> d_c, cl = m & ((1u << d_c) - 1u);
-        const uint32_t row = rowbase | rl;
-        const uint32_t lo0 = colbase | (cl << 4) | ((uint32_t)lc << 2);
-        const uint32_t s0 = (row << KC) | lo0;
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        tile_rhs<false>(sp, spaces, S, KC, KR, row, lo0, acc);
-        {
-            constexpr int NB = TILE_NBA;
-            uint32_t mm = cH;
-            while (mm) {
-                double r[NB][4], y[NB][4];
-#pragma unroll
-                for (int e = 0; e < NB; ++e) {
-                    const bool on = mm != 0u;
-                    const int a = on ? __ffs(mm) + 3 + d_c : 4;
-                    mm &= mm - 1;
-                    const uint32_t bit = 1u << a;
-                    if (on) { ld4(c.colA[a] + (lo0 ^ bit), r[e]); ld4(v + (s0 ^ bit), y[e]); }
-                    else {
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) { r[e][t] = 0.0; y[e][t] = 0.0; }
-                    }
-                }
-#pragma unroll
-                for (int e = 0; e < NB; ++e)
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) acc[t] = fma(r[e][t], y[e][t], acc[t]);
-            }
-        }
-        {
-            constexpr int NB = TILE_NBB;
-            uint32_t mm = rH;
-            while (mm) {
-                double y[NB][4], k[NB];
-#pragma unroll
-                for (int e = 0; e < NB; ++e) {
-                    const bool on = mm != 0u;
-                    const int b = on ? __ffs(mm) - 1 + d_r : 0;
-                    mm &= mm - 1;
-                    const uint32_t orow = row ^ (1u << b);
-                    if (on) { k[e] = c.rowB[b][orow]; ld4(v + (((uint64_t)orow << KC) | lo0), y[e]); }
-                    else {
-                        k[e] = 0.0;
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) y[e][t] = 0.0;
-                    }
-                }
-#pragma unroll
-                for (int e = 0; e < NB; ++e)
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) acc[t] = fma(k[e], y[e][t], acc[t]);
-            }
-        }
-        if (valid) {
-            double2* o = reinterpret_cast<double2*>(Yt + rl * rs + (cl << 4) + ((uint32_t)lc << 2));
-            o[0] = make_double2(acc[0], acc[1]);
-            o[1] = make_double2(acc[2], acc[3]);
-        }
-    }
-    __syncthreads();
-    // ---- phase 2: inner levels, shared memory only ----
-    for (int j = 0; j <= d; ++j) {
-        const uint32_t offD = hsidx[d * 32 + j];
-        const uint32_t units = hsidx[d * 32 + j + 1] - offD;
-        for (uint32_t u0 = (uint32_t)w * 8u; u0 < units; u0 += 64u) {
-            const bool valid = u0 + (uint32_t)lg < units;
-            const uint32_t m = hs[offD + min(u0 + (uint32_t)lg, units - 1u)];
-            const uint32_t rl = m >> d_c, cl = m & ((1u << d_c) - 1u);
-            const uint32_t lcol = (cl << 4) | ((uint32_t)lc << 2);               // column inside the block
-            const uint32_t so = rl * rs + lcol;                                  // own tile in the shared block
-            double acc[4];
-            {
-                const double2* a2 = reinterpret_cast<const double2*>(Yt + so);
-                const double2 p0 = a2[0], p1 = a2[1];
-                acc[0] = p0.x; acc[1] = p0.y; acc[2] = p1.x; acc[3] = p1.y;
-            }
-            uint32_t mm = m;
-            while (mm) {
-                const int p = __ffs(mm) - 1;
-                mm &= mm - 1;
-                if (p < d_c) {
-                    const uint32_t scol = lcol ^ (16u << p);                     // source columns (bit cleared)
-                    const double* ys = Yt + rl * rs + scol;
-                    const double* rr = Rc + (size_t)(4 + p) * rs + scol;
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) acc[t] = fma(rr[t], ys[t], acc[t]);
-                } else {
-                    const int b = p - d_c;
-                    const uint32_t srl = rl ^ (1u << b);                         // source row (bit cleared)
-                    const double* ys = Yt + srl * rs + lcol;
-                    const double k = Rr[(size_t)b * nr + srl];
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) acc[t] = fma(k, ys[t], acc[t]);
-                }
-            }
-            double val[4];
-            tile_tail_fwd_s(Rc, rs, dAc, dBr[rl], lcol, lane, acc, val);
-            if (valid) {
-                double2* o = reinterpret_cast<double2*>(Yt + so);
-                o[0] = make_double2(val[0], val[1]);
-                o[1] = make_double2(val[2], val[3]);
-                st4(v + (((uint64_t)(rowbase | rl) << KC) | colbase | lcol), val[0], val[1], val[2], val[3]);
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// Adjoint tile solve of a pair with the group-B marginal statistics fused in.  The adjoint pass already holds, for
-// every state s and every row bit b not in s, the value x[s + b]; with y[s] (one more 32-byte load) the lane adds
-//     stB[1+b][uB] += sum_uA y[s] x[s + b]      stB[0][uB] += sum_uA x[s] y[s]
-// which saves the separate k_stats_b pass (one more full read of x and y plus KB/2 re-reads of x through L2).
-// A CTA is G row groups x C column blocks (G C <= 32) of one (lA, lB) split: the per-tile sums are parked in shared
-// memory, added over the CTA's column blocks in a fixed order and written to the partial table `slot` of the space
-// (every row receives every slot exactly once, no atomics; k_stats_reduce adds the slots).
-// item: a = lA | lB << 8, b = first row group, c = column chunk k | slot << 16
-constexpr int ADJB_MAXE = 17;                       // g + up to 16 row bits (pairs with plain tables have KB <= MAXT)
-
-__device__ __forceinline__ double group4_sum(double v)
-{
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    return v;
-}
-
-__global__ void __launch_bounds__(256, ADJB_CTAS)
-k_solve_tile_adjb(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs, const uint32_t* __restrict__ hs,
-                  const uint32_t* __restrict__ hsidx, double* __restrict__ S)
-{
-    __shared__ TileCtx ctx;
-    __shared__ double pb[32][8][ADJB_MAXE];
-    const Item sg = segs[blockIdx.x];
-    const SpaceDev& sp = spaces[sg.space];
-    tile_ctx_build(ctx, sp, S, threadIdx.x);
-    for (int t = threadIdx.x; t < 32 * 8 * ADJB_MAXE; t += blockDim.x) (&pb[0][0][0])[t] = 0.0;
-    __syncthreads();
-    const TileCtx& c = ctx;
-    const int KC = c.KC, KR = c.KR;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, lc = lane & 3, lg = lane >> 2;
-    const uint32_t lA = sg.a & 255u, lB = (sg.a >> 8) & 255u;
-    const uint32_t kch = sg.c & 0xffffu, slot = sg.c >> 16;
-    const uint32_t offA = hsidx[(KC - 4) * 32 + lA], nA = hsidx[(KC - 4) * 32 + lA + 1] - offA;
-    const uint32_t offB = hsidx[KR * 32 + lB], nB = hsidx[KR * 32 + lB + 1] - offB;
-    const uint32_t nBg = (nB + 7u) >> 3;
-    uint32_t C = 32;                                   // column blocks per row group in this CTA
-    if (nA < 32u) { C = 1; while (C < nA) C <<= 1; }
-    const uint32_t G = 32u / C;
-    double* v = S + sp.x_off;
-    const double* yv = S + sp.y_off;
-    for (uint32_t q = w; q < 32u; q += 8) {
-        const uint32_t g = q / C, ci = q - g * C;
-        const uint32_t jB = sg.b + g, iA = kch * 32u + ci;
-        if (jB >= nBg || iA >= nA) continue;           // uniform over the warp
-        const uint32_t ri = jB * 8u + (uint32_t)lg;
-        const bool valid = ri < nB;
-        const uint32_t cA = hs[offA + iA];
-        const uint32_t row = hs[offB + min(ri, nB - 1u)];
-        const uint32_t lo0 = (cA << 4) | ((uint32_t)lc << 2);
-        const uint32_t s0 = (row << KC) | lo0;
-        double acc[4] = {0.0, 0.0, 0.0, 0.0}, y4[4];
-        ld4(yv + s0, y4);
-        tile_rhs<true>(sp, spaces, S, KC, KR, row, lo0, acc);
-        // column bits >= 4
-        {
-            constexpr int NB = TILE_NBA;
-            uint32_t m = ~cA & ((1u << (KC - 4)) - 1u);
-            while (m) {
-                double r[NB][4], y[NB][4];
-#pragma unroll
-                for (int e = 0; e < NB; ++e) {
-                    const bool on = m != 0u;
-                    const int a = on ? __ffs(m) + 3 : 4;
-                    m &= m - 1;
-                    if (on) { ld4(c.colA[a] + lo0, r[e]); ld4(v + (s0 | (1u << a)), y[e]); }
-                    else {
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) { r[e][t] = 0.0; y[e][t] = 0.0; }
-                    }
-                }
-#pragma unroll
-                for (int e = 0; e < NB; ++e)
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) acc[t] = fma(r[e][t], y[e][t], acc[t]);
-            }
-        }
-        // row bits: solve edge and statistic from the same loaded values
-        {
-            constexpr int NB = TILE_NBB;
-            uint32_t m = ~row & ((1u << KR) - 1u);
-            while (m) {
-                double y[NB][4], k[NB];
-                int bq[NB];
-#pragma unroll
-                for (int e = 0; e < NB; ++e) {
-                    const bool on = m != 0u;
-                    const int b = on ? __ffs(m) - 1 : 0;
-                    m &= m - 1;
-                    bq[e] = on ? b : -1;
-                    if (on) {
-                        k[e] = c.rowB[b][row];
-                        ld4(v + (((uint64_t)(row | (1u << b)) << KC) | lo0), y[e]);
-                    } else {
-                        k[e] = 0.0;
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) y[e][t] = 0.0;
-                    }
-                }
-#pragma unroll
-                for (int e = 0; e < NB; ++e) {
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) acc[t] = fma(k[e], y[e][t], acc[t]);
-                    const double d = group4_sum(fma(y4[3], y[e][3], fma(y4[2], y[e][2], fma(y4[1], y[e][1], y4[0] * y[e][0]))));
-                    if (lc == 0 && bq[e] >= 0) pb[q][lg][1 + bq[e]] = d;
-                }
-            }
-        }
-        double val[4];
-        tile_tail<true, false>(c, row, lo0, lane, acc, val);
-        const double gsum = group4_sum(fma(y4[3], val[3], fma(y4[2], val[2], fma(y4[1], val[1], y4[0] * val[0]))));
-        if (lc == 0) pb[q][lg][0] = gsum;
-        if (valid) st4(v + s0, val[0], val[1], val[2], val[3]);
-    }
-    __syncthreads();
-    // add the CTA's column blocks (fixed order) and write the partial table of this slot
-    const uint32_t NBr = 1u << KR;
-    double* out = S + sp.stPB + (uint64_t)slot * (KR + 1) * NBr;
-    for (uint32_t t = threadIdx.x; t < G * 8u * (uint32_t)(KR + 1); t += blockDim.x) {
-        const uint32_t e = t % (uint32_t)(KR + 1), rr = (t / (uint32_t)(KR + 1)) & 7u, g = t / ((uint32_t)(KR + 1) * 8u);
-        const uint32_t jB = sg.b + g;
-        const uint32_t ri = jB * 8u + rr;
-        if (jB >= nBg || ri >= nB) continue;
-        double s = 0.0;
-        for (uint32_t ci = 0; ci < C; ++ci) s += pb[g * C + ci][rr][e];
-        out[(uint64_t)e * NBr + hs[offB + ri]] = s;
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// Row-block solve (big tier, at most RB_MAXKC column bits).  A CTA owns R rows of one row level lB together with ALL
-// their columns, R * 2^KC <= RB_STATES values held in shared memory:
-//   phase 1  thread = four columns of a row: right-hand side plus every edge on a row bit (sources are rows finished
-//            by earlier launches; fully coalesced 32-byte loads, one scalar rate per edge for a pair)
-//   phase 2  the column lattice of the R rows is solved inside shared memory, level after level of the column-block
-//            index (__syncthreads between levels); a warp takes 8 (row, column block) units of 16 states, edges on
-//            column bits >= 4 read shared memory, bits 0..3 are resolved as in the tile kernel (tile_tail)
-// Against the tile kernel this removes the global reads of the column edges and needs one launch per ROW level only.
-constexpr int RB_STATES = 8192;
-constexpr int RB_MAXKC = 13;
-constexpr int RB_THREADS = 256;
-
-__device__ __forceinline__ bool rowblock_space(const SpaceDev& sp)
-{
-    if (!tiled_space(sp)) return false;
-    return (sp.kind == K_JOINT ? sp.KA : sp.splitA) <= RB_MAXKC;
-}
-
-template <bool ADJ, bool PROD>
-__device__ __forceinline__ void solve_rows(const SpaceDev& sp, const SpaceDev* __restrict__ spaces, const TileCtx& c,
-                                           double* __restrict__ S, const uint32_t* __restrict__ hs,
-                                           const uint32_t* __restrict__ hsidx, uint32_t lB, uint32_t first, uint32_t R,
-                                           double* __restrict__ Yt)
-{
-    const int KC = c.KC, KR = c.KR;
-    const uint32_t NC = 1u << KC;
-    const uint32_t offB = hsidx[KR * 32 + lB] + first;
+    double* sm = blk_sm + w * BLK_DOUBLES;
     double* v = S + (ADJ ? sp.x_off : sp.y_off);
-    // ---- phase 1 ----
-    const uint32_t total = R << KC;
-    for (uint32_t idx = threadIdx.x * 4u; idx < total; idx += RB_THREADS * 4u) {
-        const uint32_t r = idx >> KC, lo0 = idx & (NC - 1u);
-        const uint32_t row = hs[offB + r];
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        tile_rhs<ADJ>(sp, spaces, S, KC, KR, row, lo0, acc);
-        tile_row_edges<ADJ, PROD>(c, v, row, lo0, acc);
-        double2* o = reinterpret_cast<double2*>(Yt + idx);
-        o[0] = make_double2(acc[0], acc[1]);
-        o[1] = make_double2(acc[2], acc[3]);
-    }
-    __syncthreads();
-    // ---- phase 2 ----
-    const int kbA = KC - 4;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, lc = lane & 3;
-    for (int q = 0; q <= kbA; ++q) {
-        const int lA = ADJ ? kbA - q : q;
-        const uint32_t offA = hsidx[kbA * 32 + lA];
-        const uint32_t nA = hsidx[kbA * 32 + lA + 1] - offA;
-        const uint32_t units = nA * R;
-        for (uint32_t u0 = (uint32_t)w * 8u; u0 < units; u0 += (RB_THREADS / 32) * 8u) {
-            const uint32_t u = u0 + (uint32_t)(lane >> 2);
-            const bool valid = u < units;
-            const uint32_t uu = valid ? u : units - 1u;
-            const uint32_t iA = uu / R, r = uu - iA * R;
-            const uint32_t cA = hs[offA + iA];
-            const uint32_t row = hs[offB + r];
-            const uint32_t lo0 = (cA << 4) | ((uint32_t)lc << 2);
-            double* yr = Yt + ((size_t)r << KC);
-            double acc[4];
-            {
-                const double2* a2 = reinterpret_cast<const double2*>(yr + lo0);
-                const double2 p0 = a2[0], p1 = a2[1];
-                acc[0] = p0.x; acc[1] = p0.y; acc[2] = p1.x; acc[3] = p1.y;
-            }
-            // column bits >= 4: values from shared memory, rates from the column tables
-            uint32_t m = ADJ ? (~cA & ((1u << kbA) - 1u)) : cA;
-            constexpr int NB = 2;
-            while (m) {
-                double rr[NB][4], yy[NB][4], k[NB];
-#pragma unroll
-                for (int e = 0; e < NB; ++e) {
-                    const bool on = m != 0u;
-                    const int a = on ? __ffs(m) + 3 : 4;
-                    m &= m - 1;
-                    const uint32_t bit = 1u << a;
-                    k[e] = 1.0;
-                    if (on) {
-                        ld4(c.colA[a] + (ADJ ? lo0 : (lo0 ^ bit)), rr[e]);
-                        const double2* y2 = reinterpret_cast<const double2*>(yr + (lo0 ^ bit));
-                        const double2 p0 = y2[0], p1 = y2[1];
-                        yy[e][0] = p0.x; yy[e][1] = p0.y; yy[e][2] = p1.x; yy[e][3] = p1.y;
-                        if (PROD) k[e] = c.rowA[a][row];
-                    } else {
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) { rr[e][t] = 0.0; yy[e][t] = 0.0; }
-                    }
-                }
-#pragma unroll
-                for (int e = 0; e < NB; ++e)
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) acc[t] = fma(PROD ? rr[e][t] * k[e] : rr[e][t], yy[e][t], acc[t]);
-            }
-            double val[4];
-            tile_tail<ADJ, PROD>(c, row, lo0, lane, acc, val);
-            if (valid) {
-                double2* o = reinterpret_cast<double2*>(yr + lo0);
-                o[0] = make_double2(val[0], val[1]);
-                o[1] = make_double2(val[2], val[3]);
-                st4(v + (((uint64_t)row << KC) | lo0), val[0], val[1], val[2], val[3]);
-            }
+    const uint32_t off = hsidx[ctx.KO * 32 + it.a] + it.b;
+    const uint32_t omax = (1u << ctx.KO) - 1u;
+    const BlkRhs<ADJ> rhs{sp, spaces, S};
+    for (uint32_t k = w; k < it.c; k += BLKW) {
+        const uint32_t o = hs[off + k];
+        BlkLane L;
+        blk_lane_setup<ADJ>(ctx, blk_outer_mask(ctx, o), lane, L);
+        const uint32_t omask = ADJ ? (~o & omax) : o;
+#pragma unroll 1
+        for (int t = 0; t < BLK_STEPS; ++t) {
+            blk_lane_step<ADJ>(ctx, L, lane, t, omask, v, sm, sm, rhs);
+            __syncwarp();
         }
-        __syncthreads();
     }
 }
 
-// item: space, a = lB | rows << 8, b = first row of the item inside level lB
-template <bool ADJ>
-__global__ void __launch_bounds__(RB_THREADS, 3)
-k_solve_rows(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs, const uint32_t* __restrict__ hs,
-             const uint32_t* __restrict__ hsidx, double* __restrict__ S)
-{
-    extern __shared__ double Yt[];
-    __shared__ TileCtx ctx;
-    const Item sg = segs[blockIdx.x];
-    const SpaceDev& sp = spaces[sg.space];
-    tile_ctx_build(ctx, sp, S, threadIdx.x);
-    __syncthreads();
-    const uint32_t lB = sg.a & 255u, R = sg.a >> 8;
-    if (sp.kind != K_JOINT) solve_rows<ADJ, true>(sp, spaces, ctx, S, hs, hsidx, lB, sg.b, R, Yt);
-    else                    solve_rows<ADJ, false>(sp, spaces, ctx, S, hs, hsidx, lB, sg.b, R, Yt);
-}
-
-// per-patient log-likelihood (likelihood.py:316,350,384,405,438)
+// ------------------------------------------------------------------------------------------
 __global__ void k_logp(const SpaceDev* __restrict__ spaces, const uint32_t* __restrict__ list, uint32_t count,
                        const double* __restrict__ S, double* __restrict__ logp)
 {
