@@ -17,7 +17,7 @@
 using namespace mmh;
 
 static constexpr int RED_SLICES = 32;            // first stage of the gradient-partials reduction
-static constexpr size_t BLK_SMEM = (size_t)BLKW * BLK_DOUBLES * sizeof(double);
+static constexpr size_t BLK_SMEM = (size_t)BLK_CTA_DOUBLES * sizeof(double);
 static constexpr size_t FIN_SMEM = (size_t)(NACC * NR * NR + FIN_WARPS * NR * 33) * sizeof(double);
 
 static thread_local std::string g_err;
@@ -410,7 +410,8 @@ static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_da
                 lv[l].off = items.size();
                 uint64_t total = 0;
                 for (int pass = 0; pass < 2; ++pass) {
-                    const uint32_t rounds = (uint32_t)std::min<uint64_t>(8, std::max<uint64_t>(1, total / ((uint64_t)BLKW * 148)));
+                    // one block per warp unless the level is many waves deep (a block is long: coarse items leave SMs idle at the tail)
+                    const uint32_t rounds = total > 16ull * BLKW * 148 ? 2u : 1u;
                     const uint32_t per_cta = rounds * BLKW;
                     for (uint32_t i = 0; i < ck.nspaces; ++i) {
                         if (!pred(sp[i]) || !blocked(sp[i])) continue;

@@ -702,14 +702,17 @@ __device__ __forceinline__ void st4(double* __restrict__ p, double a, double b, 
 //   pair (no split tables, KA >= 3 or KA == 0): an A-bit's rate is the vector T_A[ev][uA], a B-bit's rate the scalar
 //       T_B[ev][uB]; diag = D_A[uA] + D_B[uB]
 //   single-tumour space in product form with K1 = 8: rate = T1[ev][u & 255] * T2[ev][u >> 8], full diagonal vector
-constexpr int BLKW = 6;                                  // warps (= blocks in flight) per CTA: 6 x 32 KB of shared memory
+constexpr int BLKW = 4;                                  // warps (= blocks in flight) per CTA
+// per warp: the block (32 KB) + the ring of source rows (12 KB) + the block's per-row scalars (3.5 KB); per CTA: the column profiles
+constexpr int BLK_WARP_DOUBLES = BLK_DOUBLES + BLK_NS * BLK_ROW + BLK_SC_DOUBLES;
+constexpr int BLK_CTA_DOUBLES = BLKW * BLK_WARP_DOUBLES + BLK_MAXC * BLK_ROW;
 
 __host__ __device__ __forceinline__ bool blocked_space(const SpaceDev& sp)
 {
     const int K = (int)sp.KA + (int)sp.KB;
     if (K < BIGK || sp.kind == K_PRE) return false;
-    if (sp.kind == K_JOINT) return !sp.splitA && !sp.splitB && (sp.KA >= 3 || sp.KA == 0);
-    return sp.splitA == BLK_CB;
+    if (sp.kind == K_JOINT) return !sp.splitA && !sp.splitB;
+    return sp.splitA == BLK_CB && K - BLK_CB <= BLK_MAXC;      // one column profile per non-column bit
 }
 
 __device__ __forceinline__ void blk_ctx_build(BlkCtx& c, const SpaceDev& sp, const double* __restrict__ S, int tid)
@@ -718,11 +721,11 @@ __device__ __forceinline__ void blk_ctx_build(BlkCtx& c, const SpaceDev& sp, con
     const bool joint = sp.kind == K_JOINT;
     if (tid < K) {
         BlkBit b;
-        b.pad = 0;
+        b.cidx = -1;
         if (joint) {
-            if (tid < KA) { b.P = S + sp.tabA + ((uint64_t)sp.evA[tid] << KA); b.mP = (1u << KA) - 1u; b.Q = nullptr; b.mQ = 0; b.shQ = 3; }
-            else if (KA == 0) { b.P = S + sp.tabB + ((uint64_t)sp.evB[tid] << KB); b.mP = (1u << KB) - 1u; b.Q = nullptr; b.mQ = 0; b.shQ = 3; }
-            else { b.P = nullptr; b.mP = 7u; b.Q = S + sp.tabB + ((uint64_t)sp.evB[tid - KA] << KB); b.mQ = (1u << KB) - 1u; b.shQ = (uint32_t)KA; }
+            if (tid < KA) { b.P = S + sp.tabA + ((uint64_t)sp.evA[tid] << KA); b.mP = (1u << KA) - 1u; b.Q = nullptr; b.mQ = 0; b.shQ = BLK_CB; }
+            else if (KA == 0) { b.P = S + sp.tabB + ((uint64_t)sp.evB[tid] << KB); b.mP = (1u << KB) - 1u; b.Q = nullptr; b.mQ = 0; b.shQ = BLK_CB; }
+            else { b.P = nullptr; b.mP = 1u; b.Q = S + sp.tabB + ((uint64_t)sp.evB[tid - KA] << KB); b.mQ = (1u << KB) - 1u; b.shQ = (uint32_t)KA; }
         } else {
             const int K2 = K - BLK_CB;
             const double* T1 = S + sp.tabA;
@@ -732,16 +735,17 @@ __device__ __forceinline__ void blk_ctx_build(BlkCtx& c, const SpaceDev& sp, con
         }
         c.bit[tid] = b;
     }
+    __syncthreads();
     if (tid == 0) {
         if (joint) {
             const double* dA = S + sp.tabA + ((uint64_t)ROW_D << KA);
             const double* dB = S + sp.tabB + ((uint64_t)ROW_D << KB);
-            if (KA == 0) { c.d1 = dB; c.m1 = (1u << KB) - 1u; c.d2 = dA; c.m2 = 0; c.sh2 = 0; }
+            if (KA == 0) { c.d1 = dB; c.m1 = (1u << KB) - 1u; c.d2 = dA; c.m2 = 0; c.sh2 = BLK_CB; }
             else { c.d1 = dA; c.m1 = (1u << KA) - 1u; c.d2 = dB; c.m2 = (1u << KB) - 1u; c.sh2 = (uint32_t)KA; }
         } else {
             const int K2 = K - BLK_CB;
             c.d1 = S + sp.tabA + ((uint64_t)NR << BLK_CB) + ((uint64_t)NR << K2);
-            c.m1 = (1u << K) - 1u; c.d2 = nullptr; c.m2 = 0; c.sh2 = 0;
+            c.m1 = (1u << K) - 1u; c.d2 = nullptr; c.m2 = 0; c.sh2 = BLK_CB;
         }
         blk_ctx_layout(c, K, (joint && KA > BLK_CB) ? KA : BLK_CB);
     }
@@ -757,7 +761,8 @@ __device__ __forceinline__ void blk_ctx_build(BlkCtx& c, const SpaceDev& sp, con
     __syncthreads();
 }
 
-// right-hand side of the eight states of a lane: non-zero on few chunks only (except the second phase's start vector)
+// right-hand side of the eight states s0 + blk_joff(j) of a lane: non-zero on few lanes only (except the second phase's
+// start vector), so a cheap necessary condition on the lane's states comes first
 template <bool ADJ>
 struct BlkRhs {
     const SpaceDev& sp;
@@ -767,22 +772,53 @@ struct BlkRhs {
     {
         const int KA = sp.KA, KB = sp.KB;
         const uint32_t NA = 1u << KA, NB = 1u << KB;
-        const uint32_t lo0 = s0 & (NA - 1u), row = s0 >> KA;         // pair, KA >= 3: the chunk lies in one row
+        const uint32_t hi = s0 | BLK_REGMASK;                        // the lane's states lie between s0 and hi, bitwise
         bool any;
         if (!ADJ) {
-            if (sp.kind == K_JOINT) any = KA == 0 ? s0 == 0u : (row < (1u << sp.nb) && ((row ^ lo0) & ~7u) == 0u);
+            if (sp.kind == K_JOINT) any = (s0 >> KA) < (1u << sp.nb);   // seeding inflow: rows uB < 2^nb only
             else if (sp.kind == K_PF || sp.kind == K_MF) any = true;
-            else any = s0 == 0u;
+            else any = (s0 & ~BLK_REGMASK) == 0u;
         } else {
-            if (sp.kind == K_JOINT) any = KA == 0 ? true : ((sp.has_pf && (lo0 | 7u) == NA - 1u) || (sp.has_mf && row == NB - 1u));
-            else any = (s0 | 7u) == (NA << KB) - 1u;
+            if (sp.kind == K_JOINT) any = (sp.has_pf && (hi & (NA - 1u)) == NA - 1u) || (sp.has_mf && (hi >> KA) == NB - 1u);
+            else any = hi == (NA << KB) - 1u;
         }
         if (any) {
 #pragma unroll
-            for (int t = 0; t < 8; ++t) acc[t] = ADJ ? rhs_adj(sp, spaces, S, s0 + t) : rhs_fwd(sp, spaces, S, s0 + t);
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t s = s0 + blk_joff(j);
+                acc[j] = ADJ ? rhs_adj(sp, spaces, S, s) : rhs_fwd(sp, spaces, S, s);
+            }
         }
     }
 };
+
+// ---- bulk asynchronous copy (TMA) + mbarrier, the subset this kernel needs ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE;\n"
+        "bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 // item: space, a = outer level, b = first block of that level (index into the popcount-sorted list), c = blocks
 template <bool ADJ>
@@ -790,25 +826,78 @@ __global__ void __launch_bounds__(BLKW * 32, 1)
 k_blk(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, const uint32_t* __restrict__ hs,
       const uint32_t* __restrict__ hsidx, double* __restrict__ S)
 {
-    extern __shared__ __align__(16) double blk_sm[];
+    extern __shared__ __align__(128) double blk_sm[];
     __shared__ BlkCtx ctx;
+    __shared__ BlkPlan plans[BLKW];
+    __shared__ __align__(8) uint64_t bars[BLKW][BLK_NS];
     const Item it = items[blockIdx.x];
     const SpaceDev& sp = spaces[it.space];
-    blk_ctx_build(ctx, sp, S, threadIdx.x);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    double* sm = blk_sm + w * BLK_DOUBLES;
+    if (lane == 0) {
+        for (int s = 0; s < BLK_NS; ++s) mbar_init(&bars[w][s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    blk_ctx_build(ctx, sp, S, threadIdx.x);          // ends with __syncthreads: the barriers are initialised for everybody
+    double* sm = blk_sm + w * BLK_WARP_DOUBLES;
+    double* ring = sm + BLK_DOUBLES;
+    double* sc = ring + BLK_NS * BLK_ROW;
+    double* ctab = blk_sm + BLKW * BLK_WARP_DOUBLES;
+    for (int i = threadIdx.x; i < ctx.nC * BLK_ROW; i += BLKW * 32) blk_ctab_entry(ctx, ctx.cbit[i >> BLK_CB], i & (BLK_ROW - 1), ctab);
+    __syncthreads();
     double* v = S + (ADJ ? sp.x_off : sp.y_off);
     const uint32_t off = hsidx[ctx.KO * 32 + it.a] + it.b;
-    const uint32_t omax = (1u << ctx.KO) - 1u;
     const BlkRhs<ADJ> rhs{sp, spaces, S};
+    BlkPlan& plan = plans[w];
+    uint32_t slot = 0, par = 0;                      // ring position of the next source row to consume (runs over the blocks)
     for (uint32_t k = w; k < it.c; k += BLKW) {
         const uint32_t o = hs[off + k];
+        if (lane == 0) blk_plan(ctx, o, ADJ, plan);
+        __syncwarp();
+        const int nE = plan.nE;
+        const uint32_t total = (uint32_t)BLK_Q * nE;
+        // producer state (lane 0 issues; every lane tracks it): next source row = (i_row, i_k), into ring slot i_slot
+        uint32_t issued = 0, i_row = 0, i_slot = slot;
+        int i_k = 0;
+        auto issue = [&]() {
+            if (lane == 0) {
+                const uint32_t src = blk_chunk_row<ADJ>(ctx, plan, i_row, i_k);
+                mbar_expect_tx(&bars[w][i_slot], BLK_ROW * sizeof(double));
+                bulk_g2s(ring + i_slot * BLK_ROW, v + src, BLK_ROW * sizeof(double), &bars[w][i_slot]);
+            }
+            ++issued;
+            if (++i_k == nE) { i_k = 0; ++i_row; }
+            if (++i_slot == BLK_NS) i_slot = 0;
+        };
+        while (issued < total && issued < (uint32_t)BLK_NS) issue();
+        // per-row scalars of this block (rates of the sequence / outer edges, d2), then the lane's column-bit rates
+        for (int i = lane; i < BLK_Q * (5 + nE); i += 32) blk_sc_entry<ADJ>(ctx, plan, i, sc);
         BlkLane L;
-        blk_lane_setup<ADJ>(ctx, blk_outer_mask(ctx, o), lane, L);
-        const uint32_t omask = ADJ ? (~o & omax) : o;
+        blk_lane_setup<ADJ>(ctx, plan.base, lane, L);
+        __syncwarp();
 #pragma unroll 1
-        for (int t = 0; t < BLK_STEPS; ++t) {
-            blk_lane_step<ADJ>(ctx, L, lane, t, omask, v, sm, sm, rhs);
+        for (int t = 0; t < BLK_ITERS; ++t) {
+            if (t < BLK_Q) {
+                // ---- OUTER phase: all lanes on the row of this iteration ----
+                const uint32_t q = ADJ ? (uint32_t)(BLK_Q - 1 - t) : (uint32_t)t;
+                const uint32_t s0 = L.base | blk_seq_mask(ctx, q);
+                double acc[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = 0.0;
+                rhs(s0, acc);
+                const double* scq = sc + q * BLK_SCW + BLK_SC_OUT;
+#pragma unroll 1
+                for (int e = 0; e < nE; ++e) {
+                    const int ci = plan.ecidx[e];
+                    mbar_wait(&bars[w][slot], par);
+                    blk_outer_edge(lane, scq[e], ci >= 0 ? ctab + ci * BLK_ROW : nullptr, ring + slot * BLK_ROW, acc);
+                    if (++slot == BLK_NS) { slot = 0; par ^= 1u; }
+                    __syncwarp();                    // every lane has read the slot: it can be refilled
+                    if (issued < total) issue();
+                }
+                blk_sts8(sm + q * BLK_ROW + lane * 2, acc);
+            }
+            // ---- INNER phase: skewed wavefront ----
+            blk_inner<ADJ>(ctx, L, lane, t, v, sm, sm, sc, ctab);
             __syncwarp();
         }
     }

@@ -57,7 +57,7 @@ static Space make_space(int K, int kind, int KA, std::mt19937_64& rng)
             for (uint32_t u = 0; u < (1u << (K - 8)); ++u) { double r = 1.0; for (int j = 8; j < K; ++j) if (((u >> (j - 8)) & 1u) && j != t) r *= W[t][j]; T2[u] = r; }
             sp.P[t] = T1; sp.Q[t] = T2;
         }
-        for (int t = 0; t < K; ++t) c.bit[t] = {sp.P[t].data(), sp.Q[t].data(), 255u, (1u << (K - 8)) - 1u, 8u, 0u};
+        for (int t = 0; t < K; ++t) c.bit[t] = {sp.P[t].data(), sp.Q[t].data(), 255u, (1u << (K - 8)) - 1u, 8u, -1};
         sp.d1.resize((size_t)1 << K);
         for (auto& v : sp.d1) v = 1.0 + U(rng);
         c.d1 = sp.d1.data(); c.m1 = (1u << K) - 1u; c.d2 = nullptr; c.m2 = 0; c.sh2 = 0;
@@ -69,8 +69,8 @@ static Space make_space(int K, int kind, int KA, std::mt19937_64& rng)
             const int bits = a ? KA : KB, off = a ? 0 : KA;
             std::vector<double> T((size_t)1 << bits);
             for (uint32_t u = 0; u < (1u << bits); ++u) { double r = base[t]; for (int j = 0; j < bits; ++j) if (((u >> j) & 1u) && j + off != t) r *= W[t][j + off]; T[u] = r; }
-            if (a || KA == 0) { sp.P[t] = T; c.bit[t] = {sp.P[t].data(), nullptr, (1u << bits) - 1u, 0u, 3u, 0u}; }
-            else { sp.Q[t] = T; c.bit[t] = {nullptr, sp.Q[t].data(), 7u, (1u << KB) - 1u, (uint32_t)KA, 0u}; }
+            if (a || KA == 0) { sp.P[t] = T; c.bit[t] = {sp.P[t].data(), nullptr, (1u << bits) - 1u, 0u, 8u, -1}; }
+            else { sp.Q[t] = T; c.bit[t] = {nullptr, sp.Q[t].data(), 1u, (1u << KB) - 1u, (uint32_t)KA, -1}; }
         }
         if (KA == 0) {
             sp.d1.resize((size_t)1 << KB); sp.d2.assign(1, 0.25);
@@ -128,31 +128,64 @@ static std::vector<double> reference(const Space& sp, bool adj)
 
 struct RhsArr {
     const double* b;
-    void operator()(uint32_t s0, double (&acc)[8]) const { for (int j = 0; j < 8; ++j) acc[j] = b[s0 + j]; }
+    void operator()(uint32_t s0, double (&acc)[8]) const { for (int j = 0; j < 8; ++j) acc[j] = b[s0 + blk_joff(j)]; }
 };
 
+// mirrors the orchestration of k_blk (mmh_device.cuh): ring of BLK_NS source rows filled in consumption order, OUTER phase
+// with all lanes on the row of the iteration, INNER phase skewed
 template <bool ADJ>
 static std::vector<double> emulate(const Space& sp)
 {
     const BlkCtx& c = sp.ctx;
     const uint32_t N = 1u << sp.K;
     std::vector<double> v(N, std::nan(""));                 // unsolved entries poison whatever reads them too early
-    std::vector<double> sm(BLK_DOUBLES), snap(BLK_DOUBLES);
+    std::vector<double> sm(BLK_DOUBLES), snap(BLK_DOUBLES), ring((size_t)BLK_NS * BLK_ROW);
+    std::vector<double> ctab((size_t)BLK_MAXC * BLK_ROW, std::nan("")), sc(BLK_SC_DOUBLES);
+    if (c.nC > BLK_MAXC) { std::printf("too many column profiles\n"); std::exit(2); }
+    for (int t = 0; t < c.K; ++t)
+        if (c.bit[t].cidx >= 0) for (int col = 0; col < BLK_ROW; ++col) blk_ctab_entry(c, t, col, ctab.data());
     RhsArr rhs{sp.rhs.data()};
     const int KO = c.KO;
+    uint32_t cons = 0;                                      // running over the blocks of the "warp", like on the device
     for (int lv = 0; lv <= KO; ++lv) {
         const int level = ADJ ? KO - lv : lv;
         for (uint32_t o = 0; o < (1u << KO); ++o) {
             if (__builtin_popcount(o) != level) continue;
-            const uint32_t om = blk_outer_mask(c, o);
-            const uint32_t omask = ADJ ? (~o & ((1u << KO) - 1u)) : o;
+            BlkPlan plan;
+            blk_plan(c, o, ADJ, plan);
+            const uint32_t total = (uint32_t)BLK_Q * plan.nE, cons0 = cons;
+            uint32_t issued = 0;
+            auto issue = [&]() {
+                const uint32_t src = blk_chunk_row<ADJ>(c, plan, issued / plan.nE, (int)(issued % plan.nE));
+                std::memcpy(&ring[(size_t)((cons0 + issued) % BLK_NS) * BLK_ROW], &v[src], BLK_ROW * sizeof(double));
+                ++issued;
+            };
+            while (issued < total && issued < (uint32_t)BLK_NS) issue();
             for (auto& x : sm) x = std::nan("");
+            for (auto& x : sc) x = std::nan("");
+            for (int idx = 0; idx < BLK_Q * (5 + plan.nE); ++idx) blk_sc_entry<ADJ>(c, plan, idx, sc.data());
             BlkLane L[32];
-            for (int lane = 0; lane < 32; ++lane) blk_lane_setup<ADJ>(c, om, lane, L[lane]);
-            for (int t = 0; t < BLK_STEPS; ++t) {
+            for (int lane = 0; lane < 32; ++lane) blk_lane_setup<ADJ>(c, plan.base, lane, L[lane]);
+            for (int t = 0; t < BLK_ITERS; ++t) {
+                if (t < BLK_Q) {
+                    const uint32_t q = ADJ ? BLK_Q - 1 - t : t;
+                    double acc[32][8];
+                    for (int lane = 0; lane < 32; ++lane) {
+                        for (int j = 0; j < 8; ++j) acc[lane][j] = 0.0;
+                        rhs(L[lane].base | blk_seq_mask(c, q), acc[lane]);
+                    }
+                    for (int k = 0; k < plan.nE; ++k) {
+                        const double* slot = &ring[(size_t)(cons % BLK_NS) * BLK_ROW];
+                        for (int lane = 0; lane < 32; ++lane)
+                            blk_outer_edge(lane, sc[q * BLK_SCW + BLK_SC_OUT + k],
+                                           plan.ecidx[k] >= 0 ? &ctab[(size_t)plan.ecidx[k] * BLK_ROW] : nullptr, slot, acc[lane]);
+                        ++cons;
+                        if (issued < total) issue();
+                    }
+                    for (int lane = 0; lane < 32; ++lane) blk_sts8(&sm[(size_t)q * BLK_ROW + lane * 2], acc[lane]);
+                }
                 snap = sm;
-                for (int lane = 0; lane < 32; ++lane)
-                    blk_lane_step<ADJ>(c, L[lane], lane, t, omask, v.data(), snap.data(), sm.data(), rhs);
+                for (int lane = 0; lane < 32; ++lane) blk_inner<ADJ>(c, L[lane], lane, t, v.data(), snap.data(), sm.data(), sc.data(), ctab.data());
             }
         }
     }
@@ -174,14 +207,15 @@ int main()
     std::mt19937_64 rng(12345);
     struct Case { int K, kind, KA; };
     const Case cases[] = {{13, 0, 0}, {15, 0, 0}, {13, 1, 9}, {14, 1, 8}, {15, 1, 11}, {14, 1, 12}, {13, 1, 3}, {14, 1, 5},
-                          {13, 1, 0}, {14, 1, 14}, {16, 1, 10}, {13, 1, 13}, {16, 0, 0}};
+                          {13, 1, 0}, {14, 1, 14}, {16, 1, 10}, {13, 1, 13}, {16, 0, 0}, {13, 1, 1}, {14, 1, 2}, {14, 1, 6},
+                          {15, 1, 7}, {17, 1, 9}};
     int bad = 0;
     for (const Case& cs : cases) {
         Space sp = make_space(cs.K, cs.kind, cs.KA, rng);
         const double ef = max_rel(emulate<false>(sp), reference(sp, false));
         const double ea = max_rel(emulate<true>(sp), reference(sp, true));
-        std::printf("K=%d kind=%d KA=%d seqdep=%02x seq=[%d %d %d %d]  fwd %.2e  adj %.2e\n", cs.K, cs.kind, cs.KA, sp.ctx.seqdep,
-                    sp.ctx.seq[0], sp.ctx.seq[1], sp.ctx.seq[2], sp.ctx.seq[3], ef, ea);
+        std::printf("K=%d kind=%d KA=%d seqdep=%02x seq=[%d %d %d %d] nC=%d d1row=%d d2mode=%d  fwd %.2e  adj %.2e\n", cs.K, cs.kind, cs.KA,
+                    sp.ctx.seqdep, sp.ctx.seq[0], sp.ctx.seq[1], sp.ctx.seq[2], sp.ctx.seq[3], sp.ctx.nC, sp.ctx.d1row, sp.ctx.d2mode, ef, ea);
         if (!(ef < 1e-12) || !(ea < 1e-12)) ++bad;
     }
     std::printf(bad ? "FAILED %d\n" : "OK\n", bad);
