@@ -410,8 +410,10 @@ static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_da
                 lv[l].off = items.size();
                 uint64_t total = 0;
                 for (int pass = 0; pass < 2; ++pass) {
-                    // one block per warp unless the level is many waves deep (a block is long: coarse items leave SMs idle at the tail)
-                    const uint32_t rounds = total > 16ull * BLKW * 148 ? 2u : 1u;
+                    // one block per warp on thin levels (latency), 2-4 per warp once the level is several waves deep: the
+                    // per-CTA setup and the first block's table are amortised, the next block's table is prefetched
+                    const uint64_t wave = (uint64_t)BLKW * 148;
+                    const uint32_t rounds = total <= wave ? 1u : total <= 6 * wave ? 2u : 4u;
                     const uint32_t per_cta = rounds * BLKW;
                     for (uint32_t i = 0; i < ck.nspaces; ++i) {
                         if (!pred(sp[i]) || !blocked(sp[i])) continue;

@@ -48,10 +48,12 @@ constexpr int BLK_Q = 1 << BLK_SB;              // rows of a block
 constexpr int BLK_ROW = 1 << BLK_CB;            // doubles per row
 constexpr int BLK_DOUBLES = BLK_Q * BLK_ROW;    // 4096 doubles = 32 KB per warp
 constexpr int BLK_ITERS = BLK_Q + 5;            // skew: 5 fill / drain iterations
-constexpr int BLK_NS = 6;                       // ring slots (one source row = 2 KB each)
+constexpr int BLK_NS = 5;                       // ring slots (one source row = 2 KB each)
 constexpr uint32_t BLK_REGMASK = 0xC1u;         // register bits of a lane's eight states: positions 0, 6, 7
-constexpr int BLK_MAXC = 16;                    // column-profile vectors of a space (256 doubles each, shared by the CTA)
-constexpr int BLK_SCW = 28;                     // per-row scalars of a block: [8..11] sequence-bit edges, [12] diagonal part, [13..] outer edges
+constexpr int BLK_MAXC = 15;                    // column-profile vectors of a space (256 doubles each, shared by the CTA)
+constexpr int BLK_MAXKO = 11;                   // outer bits (K <= 23)
+// per-row scalars of a block: [0..7] column-bit edges, [8..11] sequence-bit edges, [12] diagonal part, [13..] outer edges
+constexpr int BLK_SCW = 13 + BLK_MAXKO;
 constexpr int BLK_SC_SEQ = 8, BLK_SC_D2 = 12, BLK_SC_OUT = 13;
 constexpr int BLK_SC_DOUBLES = BLK_Q * BLK_SCW;
 
@@ -70,15 +72,15 @@ struct BlkCtx {
     const double* d2;
     uint32_t m1, m2, sh2;
     int K, KO;
-    uint32_t seqdep;                            // column bits whose rate depends on the sequence bits (mask over bits 0..7)
     int nC;                                     // column-profile vectors in use
     int d1row;                                  // 1: d1 depends on the row of the block (read per row), 0: eight values per lane and block
     int d2mode;                                 // 0: no d2, 1: one scalar per row (sh2 >= 8), 2: depends on column bits (read per piece)
+    int simple;                                 // 1: no sequence bit has a column profile, d1 per block, d2 per row (a pair whose columns are
+                                                //    group-A bits and whose sequence bits are group-B bits): the fast instantiation
     uint8_t seq[BLK_SB];                        // positions of the sequence bits, ascending
     uint8_t out[BLK_MAXBITS];                   // positions of the outer bits, ascending
     uint32_t seqm[BLK_Q];                       // index offset of row q of a block (its sequence bits)
     uint8_t cbit[BLK_MAXC];                     // bit position of every column-profile vector
-    double cs[BLK_Q][BLK_CB + 1];               // rate_t(u | seq(q)) / rate_t(u) for column bit t (+1: padding against bank conflicts)
 };
 
 // ---- small helpers ------------------------------------------------------------------------------------------
@@ -216,41 +218,55 @@ MMH_HD void blk_inv8(const double (&d)[8], double (&inv)[8])
     inv[4] = r45 * d[5]; inv[5] = r45 * d[4]; inv[6] = r67 * d[7]; inv[7] = r67 * d[6];
 }
 
-// ---- per-lane state of one block ---------------------------------------------------------------------------
-// Rates of the column-bit edges of the lane's eight states at row 0 of the block (the sequence bits only scale them:
-// BlkCtx::cs).  Forward: edges ENDING in the lane's states; adjoint: edges STARTING there.
+// ---- per-lane constants of a space and per-lane state of a block -----------------------------------------
+// Column-bit edges: rate_c(u) = profile_c(columns of u) * scalar_c(u with the column bits cleared), profile_c(col) =
+// rate_c(col) / rate_c(0).  The profile values of the lane's eight states are constants of the SPACE (registers, set
+// once per CTA); the scalar is a per-row entry of the block's table.  Forward: edges ENDING in the lane's states;
+// adjoint: edges STARTING there.
 struct BlkLane {
-    uint32_t base;                              // outer bits of the block | lane << 1
     double Rr[3][4];                            // register bits (positions 0, 6, 7): edge k of bit b, in the order of the source states lacking b
     double RL[5][8];                            // lane bits (positions 1..5); 0 where the lane has no such edge
-    double d1v[8];                              // d1 part of the diagonal of the lane's states (when it is the same for every row)
+    uint32_t base;                              // per block: outer bits of the block | lane << 1
+    double d1v[8];                              // per block: d1 part of the diagonal of the lane's states (when the same for every row)
 };
 
 template <bool ADJ>
-MMH_HD void blk_lane_setup(const BlkCtx& c, uint32_t outer_mask, int lane, BlkLane& L)
+MMH_HD void blk_lane_consts(const BlkCtx& c, int lane, BlkLane& L)
 {
-    const uint32_t u0 = outer_mask | ((uint32_t)lane << 1);
-    L.base = u0;
+    const uint32_t u0 = (uint32_t)lane << 1;
     {
         double r[8];
+        double n = 1.0 / blk_rate1(c.bit[0], 0u);
         blk_rate8(c.bit[0], u0, r);
-        L.Rr[0][0] = r[0]; L.Rr[0][1] = r[2]; L.Rr[0][2] = r[4]; L.Rr[0][3] = r[6];      // j: 0->1 2->3 4->5 6->7
+        L.Rr[0][0] = r[0] * n; L.Rr[0][1] = r[2] * n; L.Rr[0][2] = r[4] * n; L.Rr[0][3] = r[6] * n;      // j: 0->1 2->3 4->5 6->7
+        n = 1.0 / blk_rate1(c.bit[6], 0u);
         blk_rate8(c.bit[6], u0, r);
-        L.Rr[1][0] = r[0]; L.Rr[1][1] = r[1]; L.Rr[1][2] = r[4]; L.Rr[1][3] = r[5];      // j: 0->2 1->3 4->6 5->7
+        L.Rr[1][0] = r[0] * n; L.Rr[1][1] = r[1] * n; L.Rr[1][2] = r[4] * n; L.Rr[1][3] = r[5] * n;      // j: 0->2 1->3 4->6 5->7
+        n = 1.0 / blk_rate1(c.bit[7], 0u);
         blk_rate8(c.bit[7], u0, r);
-        L.Rr[2][0] = r[0]; L.Rr[2][1] = r[1]; L.Rr[2][2] = r[2]; L.Rr[2][3] = r[3];      // j: 0->4 1->5 2->6 3->7
+        L.Rr[2][0] = r[0] * n; L.Rr[2][1] = r[1] * n; L.Rr[2][2] = r[2] * n; L.Rr[2][3] = r[3] * n;      // j: 0->4 1->5 2->6 3->7
     }
 #pragma unroll
     for (int a = 0; a < 5; ++a) {
         const uint32_t bit = 2u << a;
         const bool has = (u0 & bit) != 0u;
         const bool edge = ADJ ? !has : has;      // forward: the edge comes from l ^ a (which lacks the bit); adjoint: it goes there
-        if (edge) blk_rate8(c.bit[1 + a], u0 & ~bit, L.RL[a]);
-        else {
+        if (edge) {
+            const double n = 1.0 / blk_rate1(c.bit[1 + a], 0u);
+            blk_rate8(c.bit[1 + a], u0 & ~bit, L.RL[a]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) L.RL[a][j] *= n;
+        } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) L.RL[a][j] = 0.0;
         }
     }
+}
+
+MMH_HD void blk_lane_block(const BlkCtx& c, uint32_t outer_mask, int lane, BlkLane& L)
+{
+    const uint32_t u0 = outer_mask | ((uint32_t)lane << 1);
+    L.base = u0;
     if (!c.d1row) {
 #pragma unroll
         for (int pc = 0; pc < 4; ++pc) blk_ldg2(c.d1 + ((u0 + pc * 64) & c.m1), L.d1v[2 * pc], L.d1v[2 * pc + 1]);
@@ -276,7 +292,9 @@ MMH_HD void blk_outer_edge(int lane, double sc, const double* cv, const double* 
 
 // INNER phase of one lane at iteration t: finish row t - popcount(lane) (adjoint: mirrored).  `sm_rd` / `sm_wr` are the
 // block's shared memory (the same pointer on the device; the host emulation reads from a snapshot of the iteration start).
-template <bool ADJ>
+// Straight-line code: an edge that does not exist for this lane / row has rate 0 and reads a finite value (the block's
+// memory never holds anything but zeros, partial sums and solved values).
+template <bool ADJ, bool SIMPLE>
 MMH_HD void blk_inner(const BlkCtx& c, const BlkLane& L, int lane, int t, double* __restrict__ v,
                       const double* sm_rd, double* sm_wr, const double* sc, const double* ctab)
 {
@@ -288,7 +306,7 @@ MMH_HD void blk_inner(const BlkCtx& c, const BlkLane& L, int lane, int t, double
     const double* scq = sc + q * BLK_SCW;
     // the diagonal first: when it has to come from global memory its latency hides behind the edges below
     double d[8];
-    if (c.d1row) {
+    if (!SIMPLE && c.d1row) {
 #pragma unroll
         for (int pc = 0; pc < 4; ++pc) blk_ldg2(c.d1 + ((s0 + pc * 64) & c.m1), d[2 * pc], d[2 * pc + 1]);
     } else {
@@ -300,34 +318,22 @@ MMH_HD void blk_inner(const BlkCtx& c, const BlkLane& L, int lane, int t, double
     // ---- sequence bits: rows of this block the lane finished at earlier iterations ----
 #pragma unroll
     for (int i = 0; i < BLK_SB; ++i) {
-        const bool set = (q >> i) & 1;
-        if (ADJ ? !set : set) {
-            const int ci = c.bit[c.seq[i]].cidx;
-            blk_outer_edge(lane, scq[BLK_SC_SEQ + i], ci >= 0 ? ctab + ci * BLK_ROW : nullptr,
-                           sm_rd + (q ^ (1 << i)) * BLK_ROW, acc);
-        }
+        const int ci = SIMPLE ? -1 : c.bit[c.seq[i]].cidx;
+        blk_outer_edge(lane, scq[BLK_SC_SEQ + i], ci >= 0 ? ctab + ci * BLK_ROW : nullptr, sm_rd + (q ^ (1 << i)) * BLK_ROW, acc);
     }
     // ---- lane bits: the same row of the neighbouring lanes (finished one iteration earlier) ----
-    const bool dep = c.seqdep != 0u;
 #pragma unroll
     for (int a = 0; a < 5; ++a) {
-        const bool has = (lane >> a) & 1;
-        if (ADJ ? !has : has) {
-            double y[8];
-            blk_lds8(sm_rd + q * BLK_ROW + (lane ^ (1 << a)) * 2, y);
-            if (dep) {
-                const double k = c.cs[q][1 + a];
+        double y[8];
+        blk_lds8(sm_rd + q * BLK_ROW + (lane ^ (1 << a)) * 2, y);
+        const double k = scq[1 + a];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) y[j] *= k;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = fma(L.RL[a][j], y[j], acc[j]);
-        }
+        for (int j = 0; j < 8; ++j) acc[j] = fma(L.RL[a][j], y[j] * k, acc[j]);
     }
     // ---- diagonal ----
     double inv[8];
     {
-        if (c.d2mode == 1) {
+        if (SIMPLE || c.d2mode == 1) {
             const double k = scq[BLK_SC_D2];
 #pragma unroll
             for (int j = 0; j < 8; ++j) d[j] += k;
@@ -341,8 +347,7 @@ MMH_HD void blk_inner(const BlkCtx& c, const BlkLane& L, int lane, int t, double
         blk_inv8(d, inv);
     }
     // ---- register bits (positions 0, 6, 7 <-> bits 0, 1, 2 of j) ----
-    double k0 = 1.0, k1 = 1.0, k2 = 1.0;
-    if (dep) { k0 = c.cs[q][0]; k1 = c.cs[q][6]; k2 = c.cs[q][7]; }
+    const double k0 = scq[0], k1 = scq[6], k2 = scq[7];
     double e0[4], e1[4], e2[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) { e0[k] = L.Rr[0][k] * k0; e1[k] = L.Rr[1][k] * k1; e2[k] = L.Rr[2][k] * k2; }
@@ -368,20 +373,6 @@ MMH_HD void blk_inner(const BlkCtx& c, const BlkLane& L, int lane, int t, double
     }
     blk_sts8(sm_wr + q * BLK_ROW + lane * 2, y);
     blk_stg8(v + s0, y);
-}
-
-// rates of the column bits relative to row 0 of a block (see BlkCtx::cs); call after bit[], seq[] are set
-MMH_HD void blk_ctx_cs_row(BlkCtx& c, int q)
-{
-    const uint32_t sm = blk_seq_mask(c, (uint32_t)q);
-    for (int t = 0; t < BLK_CB; ++t) {
-        const BlkBit& b = c.bit[t];
-        double num = 1.0, den = 1.0;
-        if (b.P) { num *= b.P[sm & b.mP]; den *= b.P[0]; }
-        if (b.Q) { num *= b.Q[(sm >> b.shQ) & b.mQ]; den *= b.Q[0]; }
-        c.cs[q][t] = num / den;
-    }
-    c.cs[q][BLK_CB] = 1.0;
 }
 
 // Sequence bits = the first four positions of pref, pref+1, ..., K-1, 8, 9, ... (a pair whose column bits all belong to
@@ -411,6 +402,9 @@ MMH_HD void blk_ctx_layout(BlkCtx& c, int K, int pref)
     }
     c.d1row = (c.m1 & c.seqm[BLK_Q - 1]) != 0u;
     c.d2mode = !c.d2 ? 0 : (c.sh2 >= (uint32_t)BLK_CB ? 1 : 2);
+    bool seqc = false;
+    for (int i = 0; i < BLK_SB; ++i) seqc = seqc || c.bit[c.seq[i]].cidx >= 0;
+    c.simple = (!seqc && !c.d1row && c.d2mode == 1) ? 1 : 0;
 }
 
 // number of column-profile vectors a space with these descriptors needs (host side planning uses the same rule)
@@ -419,16 +413,6 @@ MMH_HD void blk_ctab_entry(const BlkCtx& c, int t, int col, double* ctab)
 {
     const BlkBit& b = c.bit[t];
     ctab[b.cidx * BLK_ROW + col] = blk_rate1(b, (uint32_t)col) / blk_rate1(b, 0u);
-}
-
-// cs table + seqdep mask; call once bit[], seq[] are final (any thread / the host)
-MMH_HD void blk_ctx_finish(BlkCtx& c)
-{
-    c.seqdep = 0;
-    for (int q = 0; q < BLK_Q; ++q) {
-        blk_ctx_cs_row(c, q);
-        for (int t = 0; t < BLK_CB; ++t) if (c.cs[q][t] != 1.0) c.seqdep |= 1u << t;
-    }
 }
 
 // The source rows the OUTER phase of a block consumes, in order: rows in processing order, for each row the outer bits
@@ -452,32 +436,59 @@ MMH_HD void blk_plan(const BlkCtx& c, uint32_t o, bool adj, BlkPlan& p)
         m &= m - 1;
     }
 }
-// entry `idx` of the block's table of per-row scalars (idx = q * (5 + nE) + k): the rate of (row q, edge k) at the
-// row's base state with the column bits cleared -- the column profile supplies the rest -- or the d2 part of the diagonal
-template <bool ADJ>
-MMH_HD void blk_sc_entry(const BlkCtx& c, const BlkPlan& p, int idx, double* sc)
-{
-    const int per = 5 + p.nE;
-    const int q = idx / per, k = idx - q * per;
-    const uint32_t s = p.base | c.seqm[q];
-    double val = 0.0;
-    if (k < BLK_SB) {
-        const bool set = (q >> k) & 1;
-        if (ADJ ? !set : set) val = blk_rate1(c.bit[c.seq[k]], ADJ ? s : (s ^ (1u << c.seq[k])));
-        sc[q * BLK_SCW + BLK_SC_SEQ + k] = val;
-    } else if (k == BLK_SB) {
-        if (c.d2mode == 1) val = c.d2[(s >> c.sh2) & c.m2];
-        sc[q * BLK_SCW + BLK_SC_D2] = val;
-    } else {
-        const int e = k - BLK_SB - 1, t = p.epos[e];
-        sc[q * BLK_SCW + BLK_SC_OUT + e] = blk_rate1(c.bit[t], ADJ ? s : (s ^ (1u << t)));
-    }
-}
+// element offset of the source row of chunk (row_it, k): rows in processing order, edges in ascending bit order
 template <bool ADJ>
 MMH_HD uint32_t blk_chunk_row(const BlkCtx& c, const BlkPlan& p, uint32_t row_it, int k)
 {
     const uint32_t q = ADJ ? (uint32_t)(BLK_Q - 1) - row_it : row_it;
-    return (p.base | blk_seq_mask(c, q)) ^ (1u << p.epos[k]);
+    return (p.base | c.seqm[q]) ^ (1u << p.epos[k]);
+}
+
+// Entry `idx` of the block's table of per-row scalars (idx = q * (13 + nE) + k): the rate of (row q, edge k) at the row's
+// base state with the column bits cleared -- the column profile supplies the rest -- or the d2 part of the diagonal.
+// Split in two so that the device can issue the loads of the NEXT block's table one iteration before it stores them.
+struct BlkScReq { const double* a; const double* b; int dst; };       // value = (a ? *a : 1) * (b ? *b : 1), dst < 0: nothing to do
+template <bool ADJ>
+MMH_HD BlkScReq blk_sc_request(const BlkCtx& c, const BlkPlan& p, int idx)
+{
+    const int per = BLK_SC_OUT + p.nE;
+    BlkScReq r{nullptr, nullptr, -1};
+    if (idx >= BLK_Q * per) return r;
+    const int q = idx / per, k = idx - q * per;
+    const uint32_t s = p.base | c.seqm[q];
+    r.dst = q * BLK_SCW + k;
+    int t;
+    uint32_t u = s;
+    if (k < BLK_CB) t = k;                                             // column bit: scalar part of its rate in this row
+    else if (k < BLK_SC_D2) {
+        const int i = k - BLK_SC_SEQ;
+        const bool set = (q >> i) & 1;
+        t = c.seq[i];
+        if (ADJ ? set : !set) { r.dst = -2 - r.dst; return r; }        // no such edge in this row: the entry is 0
+        if (!ADJ) u = s ^ (1u << t);
+    } else if (k == BLK_SC_D2) {
+        if (c.d2mode == 1) r.a = c.d2 + ((s >> c.sh2) & c.m2);
+        else r.dst = -2 - r.dst;
+        return r;
+    } else {
+        t = p.epos[k - BLK_SC_OUT];
+        if (!ADJ) u = s ^ (1u << t);
+    }
+    const BlkBit& b = c.bit[t];
+    if (b.P) r.a = b.P + (u & b.mP);
+    if (b.Q) r.b = b.Q + ((u >> b.shQ) & b.mQ);
+    return r;
+}
+MMH_HD void blk_sc_store(const BlkScReq& r, double va, double vb, double* sc)
+{
+    if (r.dst >= 0) sc[r.dst] = va * vb;
+    else if (r.dst < -1) sc[-2 - r.dst] = 0.0;
+}
+template <bool ADJ>
+MMH_HD void blk_sc_entry(const BlkCtx& c, const BlkPlan& p, int idx, double* sc)
+{
+    const BlkScReq r = blk_sc_request<ADJ>(c, p, idx);
+    blk_sc_store(r, r.a ? *r.a : 1.0, r.b ? *r.b : 1.0, sc);
 }
 
 }  // namespace mmh

@@ -703,14 +703,16 @@ __device__ __forceinline__ void st4(double* __restrict__ p, double a, double b, 
 //       T_B[ev][uB]; diag = D_A[uA] + D_B[uB]
 //   single-tumour space in product form with K1 = 8: rate = T1[ev][u & 255] * T2[ev][u >> 8], full diagonal vector
 constexpr int BLKW = 4;                                  // warps (= blocks in flight) per CTA
-// per warp: the block (32 KB) + the ring of source rows (12 KB) + the block's per-row scalars (3.5 KB); per CTA: the column profiles
-constexpr int BLK_WARP_DOUBLES = BLK_DOUBLES + BLK_NS * BLK_ROW + BLK_SC_DOUBLES;
+// per warp: the block (32 KB) + the ring of source rows (10 KB) + the per-row scalars of this and the next block (2 x 3 KB);
+// per CTA: the column profiles (30 KB)
+constexpr int BLK_WARP_DOUBLES = BLK_DOUBLES + BLK_NS * BLK_ROW + 2 * BLK_SC_DOUBLES;
 constexpr int BLK_CTA_DOUBLES = BLKW * BLK_WARP_DOUBLES + BLK_MAXC * BLK_ROW;
 
 __host__ __device__ __forceinline__ bool blocked_space(const SpaceDev& sp)
 {
     const int K = (int)sp.KA + (int)sp.KB;
     if (K < BIGK || sp.kind == K_PRE) return false;
+    if (K - BLK_CB - BLK_SB > BLK_MAXKO) return false;
     if (sp.kind == K_JOINT) return !sp.splitA && !sp.splitB;
     return sp.splitA == BLK_CB && K - BLK_CB <= BLK_MAXC;      // one column profile per non-column bit
 }
@@ -748,15 +750,6 @@ __device__ __forceinline__ void blk_ctx_build(BlkCtx& c, const SpaceDev& sp, con
             c.m1 = (1u << K) - 1u; c.d2 = nullptr; c.m2 = 0; c.sh2 = BLK_CB;
         }
         blk_ctx_layout(c, K, (joint && KA > BLK_CB) ? KA : BLK_CB);
-    }
-    __syncthreads();
-    if (tid < BLK_Q) blk_ctx_cs_row(c, tid);
-    __syncthreads();
-    if (tid == 0) {
-        uint32_t dep = 0;
-        for (int q = 0; q < BLK_Q; ++q)
-            for (int t = 0; t < BLK_CB; ++t) if (c.cs[q][t] != 1.0) dep |= 1u << t;
-        c.seqdep = dep;
     }
     __syncthreads();
 }
@@ -820,39 +813,31 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// item: space, a = outer level, b = first block of that level (index into the popcount-sorted list), c = blocks
-template <bool ADJ>
-__global__ void __launch_bounds__(BLKW * 32, 1)
-k_blk(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, const uint32_t* __restrict__ hs,
-      const uint32_t* __restrict__ hsidx, double* __restrict__ S)
+// the block loop of one warp (SIMPLE: the instantiation without column profiles on the sequence bits, see BlkCtx::simple)
+template <bool ADJ, bool SIMPLE>
+__device__ __forceinline__ void blk_run(const BlkCtx& ctx, BlkPlan* plan2, uint64_t* bar, double* sm, const double* ctab,
+                                        double* __restrict__ v, const BlkRhs<ADJ>& rhs, const uint32_t* __restrict__ olist,
+                                        uint32_t count, int lane, int w)
 {
-    extern __shared__ __align__(128) double blk_sm[];
-    __shared__ BlkCtx ctx;
-    __shared__ BlkPlan plans[BLKW];
-    __shared__ __align__(8) uint64_t bars[BLKW][BLK_NS];
-    const Item it = items[blockIdx.x];
-    const SpaceDev& sp = spaces[it.space];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) {
-        for (int s = 0; s < BLK_NS; ++s) mbar_init(&bars[w][s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    blk_ctx_build(ctx, sp, S, threadIdx.x);          // ends with __syncthreads: the barriers are initialised for everybody
-    double* sm = blk_sm + w * BLK_WARP_DOUBLES;
     double* ring = sm + BLK_DOUBLES;
-    double* sc = ring + BLK_NS * BLK_ROW;
-    double* ctab = blk_sm + BLKW * BLK_WARP_DOUBLES;
-    for (int i = threadIdx.x; i < ctx.nC * BLK_ROW; i += BLKW * 32) blk_ctab_entry(ctx, ctx.cbit[i >> BLK_CB], i & (BLK_ROW - 1), ctab);
-    __syncthreads();
-    double* v = S + (ADJ ? sp.x_off : sp.y_off);
-    const uint32_t off = hsidx[ctx.KO * 32 + it.a] + it.b;
-    const BlkRhs<ADJ> rhs{sp, spaces, S};
-    BlkPlan& plan = plans[w];
-    uint32_t slot = 0, par = 0;                      // ring position of the next source row to consume (runs over the blocks)
-    for (uint32_t k = w; k < it.c; k += BLKW) {
-        const uint32_t o = hs[off + k];
-        if (lane == 0) blk_plan(ctx, o, ADJ, plan);
+    double* sc2 = ring + BLK_NS * BLK_ROW;
+    BlkLane L;
+    blk_lane_consts<ADJ>(ctx, lane, L);                   // column-bit rate profiles of the lane's states: once per CTA
+    for (int i = lane * 2; i < BLK_DOUBLES; i += 64) *reinterpret_cast<double2*>(sm + i) = make_double2(0.0, 0.0);
+    uint32_t slot = 0, par = 0;                           // ring position of the next source row to consume (runs over the blocks)
+    int cur = 0;
+    if ((uint32_t)w < count) {                            // table of the first block: computed in place
+        if (lane == 0) blk_plan(ctx, olist[w], ADJ, plan2[0]);
         __syncwarp();
+        for (int i = lane; i < BLK_Q * (BLK_SC_OUT + plan2[0].nE); i += 32) blk_sc_entry<ADJ>(ctx, plan2[0], i, sc2);
+    }
+    __syncwarp();
+    for (uint32_t k = w; k < count; k += BLKW) {
+        const BlkPlan& plan = plan2[cur];
+        const double* sc = sc2 + cur * BLK_SC_DOUBLES;
+        double* sc_next = sc2 + (cur ^ 1) * BLK_SC_DOUBLES;
+        const bool has_next = k + BLKW < count;
+        const uint32_t o_next = has_next ? olist[k + BLKW] : 0u;
         const int nE = plan.nE;
         const uint32_t total = (uint32_t)BLK_Q * nE;
         // producer state (lane 0 issues; every lane tracks it): next source row = (i_row, i_k), into ring slot i_slot
@@ -861,21 +846,29 @@ k_blk(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, const
         auto issue = [&]() {
             if (lane == 0) {
                 const uint32_t src = blk_chunk_row<ADJ>(ctx, plan, i_row, i_k);
-                mbar_expect_tx(&bars[w][i_slot], BLK_ROW * sizeof(double));
-                bulk_g2s(ring + i_slot * BLK_ROW, v + src, BLK_ROW * sizeof(double), &bars[w][i_slot]);
+                mbar_expect_tx(&bar[i_slot], BLK_ROW * sizeof(double));
+                bulk_g2s(ring + i_slot * BLK_ROW, v + src, BLK_ROW * sizeof(double), &bar[i_slot]);
             }
             ++issued;
             if (++i_k == nE) { i_k = 0; ++i_row; }
             if (++i_slot == BLK_NS) i_slot = 0;
         };
         while (issued < total && issued < (uint32_t)BLK_NS) issue();
-        // per-row scalars of this block (rates of the sequence / outer edges, d2), then the lane's column-bit rates
-        for (int i = lane; i < BLK_Q * (5 + nE); i += 32) blk_sc_entry<ADJ>(ctx, plan, i, sc);
-        BlkLane L;
-        blk_lane_setup<ADJ>(ctx, plan.base, lane, L);
-        __syncwarp();
+        blk_lane_block(ctx, plan.base, lane, L);
 #pragma unroll 1
         for (int t = 0; t < BLK_ITERS; ++t) {
+            // the NEXT block's table of per-row scalars is computed while this block runs: the loads of one entry per lane
+            // are issued here and stored at the end of the iteration
+            BlkScReq rq{nullptr, nullptr, -1};
+            double va = 1.0, vb = 1.0;
+            if (has_next) {
+                if (t == 0) { if (lane == 0) blk_plan(ctx, o_next, ADJ, plan2[cur ^ 1]); }
+                else {
+                    rq = blk_sc_request<ADJ>(ctx, plan2[cur ^ 1], (t - 1) * 32 + lane);
+                    if (rq.a) va = *rq.a;
+                    if (rq.b) vb = *rq.b;
+                }
+            }
             if (t < BLK_Q) {
                 // ---- OUTER phase: all lanes on the row of this iteration ----
                 const uint32_t q = ADJ ? (uint32_t)(BLK_Q - 1 - t) : (uint32_t)t;
@@ -888,7 +881,7 @@ k_blk(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, const
 #pragma unroll 1
                 for (int e = 0; e < nE; ++e) {
                     const int ci = plan.ecidx[e];
-                    mbar_wait(&bars[w][slot], par);
+                    mbar_wait(&bar[slot], par);
                     blk_outer_edge(lane, scq[e], ci >= 0 ? ctab + ci * BLK_ROW : nullptr, ring + slot * BLK_ROW, acc);
                     if (++slot == BLK_NS) { slot = 0; par ^= 1u; }
                     __syncwarp();                    // every lane has read the slot: it can be refilled
@@ -897,10 +890,41 @@ k_blk(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, const
                 blk_sts8(sm + q * BLK_ROW + lane * 2, acc);
             }
             // ---- INNER phase: skewed wavefront ----
-            blk_inner<ADJ>(ctx, L, lane, t, v, sm, sm, sc, ctab);
+            blk_inner<ADJ, SIMPLE>(ctx, L, lane, t, v, sm, sm, sc, ctab);
+            blk_sc_store(rq, va, vb, sc_next);
             __syncwarp();
         }
+        cur ^= 1;
     }
+}
+
+// item: space, a = outer level, b = first block of that level (index into the popcount-sorted list), c = blocks
+template <bool ADJ>
+__global__ void __launch_bounds__(BLKW * 32, 1)
+k_blk(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, const uint32_t* __restrict__ hs,
+      const uint32_t* __restrict__ hsidx, double* __restrict__ S)
+{
+    extern __shared__ __align__(128) double blk_sm[];
+    __shared__ BlkCtx ctx;
+    __shared__ BlkPlan plans[BLKW][2];
+    __shared__ __align__(8) uint64_t bars[BLKW][BLK_NS];
+    const Item it = items[blockIdx.x];
+    const SpaceDev& sp = spaces[it.space];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) {
+        for (int s = 0; s < BLK_NS; ++s) mbar_init(&bars[w][s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    blk_ctx_build(ctx, sp, S, threadIdx.x);          // ends with __syncthreads: the barriers are initialised for everybody
+    double* ctab = blk_sm + BLKW * BLK_WARP_DOUBLES;
+    for (int i = threadIdx.x; i < ctx.nC * BLK_ROW; i += BLKW * 32) blk_ctab_entry(ctx, ctx.cbit[i >> BLK_CB], i & (BLK_ROW - 1), ctab);
+    __syncthreads();
+    double* v = S + (ADJ ? sp.x_off : sp.y_off);
+    const uint32_t* olist = hs + hsidx[ctx.KO * 32 + it.a] + it.b;
+    const BlkRhs<ADJ> rhs{sp, spaces, S};
+    double* sm = blk_sm + w * BLK_WARP_DOUBLES;
+    if (ctx.simple) blk_run<ADJ, true>(ctx, plans[w], bars[w], sm, ctab, v, rhs, olist, it.c, lane, w);
+    else            blk_run<ADJ, false>(ctx, plans[w], bars[w], sm, ctab, v, rhs, olist, it.c, lane, w);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -84,7 +84,6 @@ static Space make_space(int K, int kind, int KA, std::mt19937_64& rng)
         }
         blk_ctx_layout(c, K, KA > 8 ? KA : 8);
     }
-    blk_ctx_finish(c);
     sp.rhs.assign((size_t)1 << K, 0.0);
     std::uniform_int_distribution<uint32_t> pick(0, (1u << K) - 1u);
     for (int i = 0; i < 40; ++i) sp.rhs[pick(rng)] = U(rng);
@@ -139,13 +138,16 @@ static std::vector<double> emulate(const Space& sp)
     const BlkCtx& c = sp.ctx;
     const uint32_t N = 1u << sp.K;
     std::vector<double> v(N, std::nan(""));                 // unsolved entries poison whatever reads them too early
-    std::vector<double> sm(BLK_DOUBLES), snap(BLK_DOUBLES), ring((size_t)BLK_NS * BLK_ROW);
+    std::vector<double> sm(BLK_DOUBLES, 0.0), snap(BLK_DOUBLES), ring((size_t)BLK_NS * BLK_ROW);    // the device zeroes a warp's block once
     std::vector<double> ctab((size_t)BLK_MAXC * BLK_ROW, std::nan("")), sc(BLK_SC_DOUBLES);
     if (c.nC > BLK_MAXC) { std::printf("too many column profiles\n"); std::exit(2); }
     for (int t = 0; t < c.K; ++t)
         if (c.bit[t].cidx >= 0) for (int col = 0; col < BLK_ROW; ++col) blk_ctab_entry(c, t, col, ctab.data());
     RhsArr rhs{sp.rhs.data()};
     const int KO = c.KO;
+    if (KO > BLK_MAXKO) { std::printf("too many outer bits\n"); std::exit(2); }
+    BlkLane L[32];
+    for (int lane = 0; lane < 32; ++lane) blk_lane_consts<ADJ>(c, lane, L[lane]);      // once per CTA on the device
     uint32_t cons = 0;                                      // running over the blocks of the "warp", like on the device
     for (int lv = 0; lv <= KO; ++lv) {
         const int level = ADJ ? KO - lv : lv;
@@ -161,11 +163,9 @@ static std::vector<double> emulate(const Space& sp)
                 ++issued;
             };
             while (issued < total && issued < (uint32_t)BLK_NS) issue();
-            for (auto& x : sm) x = std::nan("");
             for (auto& x : sc) x = std::nan("");
-            for (int idx = 0; idx < BLK_Q * (5 + plan.nE); ++idx) blk_sc_entry<ADJ>(c, plan, idx, sc.data());
-            BlkLane L[32];
-            for (int lane = 0; lane < 32; ++lane) blk_lane_setup<ADJ>(c, plan.base, lane, L[lane]);
+            for (int idx = 0; idx < BLK_Q * (BLK_SC_OUT + plan.nE); ++idx) blk_sc_entry<ADJ>(c, plan, idx, sc.data());
+            for (int lane = 0; lane < 32; ++lane) blk_lane_block(c, plan.base, lane, L[lane]);
             for (int t = 0; t < BLK_ITERS; ++t) {
                 if (t < BLK_Q) {
                     const uint32_t q = ADJ ? BLK_Q - 1 - t : t;
@@ -185,7 +185,10 @@ static std::vector<double> emulate(const Space& sp)
                     for (int lane = 0; lane < 32; ++lane) blk_sts8(&sm[(size_t)q * BLK_ROW + lane * 2], acc[lane]);
                 }
                 snap = sm;
-                for (int lane = 0; lane < 32; ++lane) blk_inner<ADJ>(c, L[lane], lane, t, v.data(), snap.data(), sm.data(), sc.data(), ctab.data());
+                for (int lane = 0; lane < 32; ++lane) {
+                    if (c.simple) blk_inner<ADJ, true>(c, L[lane], lane, t, v.data(), snap.data(), sm.data(), sc.data(), ctab.data());
+                    else blk_inner<ADJ, false>(c, L[lane], lane, t, v.data(), snap.data(), sm.data(), sc.data(), ctab.data());
+                }
             }
         }
     }
@@ -214,8 +217,8 @@ int main()
         Space sp = make_space(cs.K, cs.kind, cs.KA, rng);
         const double ef = max_rel(emulate<false>(sp), reference(sp, false));
         const double ea = max_rel(emulate<true>(sp), reference(sp, true));
-        std::printf("K=%d kind=%d KA=%d seqdep=%02x seq=[%d %d %d %d] nC=%d d1row=%d d2mode=%d  fwd %.2e  adj %.2e\n", cs.K, cs.kind, cs.KA,
-                    sp.ctx.seqdep, sp.ctx.seq[0], sp.ctx.seq[1], sp.ctx.seq[2], sp.ctx.seq[3], sp.ctx.nC, sp.ctx.d1row, sp.ctx.d2mode, ef, ea);
+        std::printf("K=%d kind=%d KA=%d simple=%d seq=[%d %d %d %d] nC=%d d1row=%d d2mode=%d  fwd %.2e  adj %.2e\n", cs.K, cs.kind, cs.KA,
+                    sp.ctx.simple, sp.ctx.seq[0], sp.ctx.seq[1], sp.ctx.seq[2], sp.ctx.seq[3], sp.ctx.nC, sp.ctx.d1row, sp.ctx.d2mode, ef, ea);
         if (!(ef < 1e-12) || !(ea < 1e-12)) ++bad;
     }
     std::printf(bad ? "FAILED %d\n" : "OK\n", bad);
