@@ -17,7 +17,6 @@
 using namespace mmh;
 
 static constexpr int RED_SLICES = 32;            // first stage of the gradient-partials reduction
-static constexpr size_t BLK_SMEM = (size_t)BLK_CTA_DOUBLES * sizeof(double);
 static constexpr size_t FIN_SMEM = (size_t)(NACC * NR * NR + FIN_WARPS * NR * 33) * sizeof(double);
 
 static thread_local std::string g_err;
@@ -42,7 +41,8 @@ struct ChunkPlan {
     Range setup, setup_wide, diag, pre, main_small, sec_small, logp, joints, st_a, st_ar, st_b, pf_lo, pf_hi, fin;
     bool wide = false;                           // some group has more than MAXT bits
     std::vector<Range> main_lv, sec_lv;          // big-tier segments per popcount level (generic kernel)
-    std::vector<Range> main_lvb, sec_lvb;        // big-tier blocks per outer level (blocked kernel, mmh_blk.cuh)
+    std::vector<Range> main_lvt, sec_lvt;        // big-tier tiles per level (tiled kernel)
+    std::vector<Range> main_lvt_adj, main_lvt_adjb;  // adjoint pass of the main tiled spaces: plain / with fused B statistics
     uint64_t scratch = 0;                        // doubles
 };
 
@@ -91,6 +91,25 @@ struct mmh_handle {
     bool comm_owned = true;
 };
 
+// pairs whose adjoint solve also produces the group-B statistics (k_solve_tile_adjb); needs splitA/splitB
+static bool fused_b(const SpaceDev& s)
+{
+    return s.kind == K_JOINT && !s.splitA && !s.splitB && s.KA >= 4 && (int)s.KA + (int)s.KB >= BIGK;
+}
+// number of partial tables: per column-block level lA one per chunk of 32 column blocks; base[lA] = first slot
+static uint32_t adjb_slots(int kbA, uint32_t* base)
+{
+    uint32_t n = 0;
+    double c = 1.0;                                     // C(kbA, lA)
+    for (int lA = 0; lA <= kbA; ++lA) {
+        if (base) base[lA] = n;
+        const uint64_t nA = (uint64_t)(c + 0.5);
+        n += (uint32_t)std::max<uint64_t>(1, (nA + 31) / 32);
+        c = c * (kbA - lA) / (lA + 1);
+    }
+    return n;
+}
+
 static uint64_t space_scratch(SpaceDev& s, uint64_t off)
 {
     const uint64_t NA = 1ull << s.KA, NB = 1ull << s.KB, N = NA * NB;
@@ -102,8 +121,6 @@ static uint64_t space_scratch(SpaceDev& s, uint64_t off)
     auto table = [&](int KG, uint8_t& split) {
         if (KG <= max_full) { split = 0; return take((uint64_t)NR << KG); }
         split = (uint8_t)((KG + 1) / 2);             // rate(i,u) = T1[i][u_lo] * T2[i][u_hi] + full special-row vectors
-        // big single-tumour spaces: the low table covers exactly the eight column bits of the blocked solve
-        if (s.kind != K_JOINT && s.kind != K_PRE && KG >= BIGK) split = (uint8_t)BLK_CB;
         return take(((uint64_t)NR << split) + ((uint64_t)NR << (KG - split)) + ((has_diag_tables ? 3ull : 1ull) << KG));
     };
     s.splitA = s.splitB = 0;
@@ -121,6 +138,7 @@ static uint64_t space_scratch(SpaceDev& s, uint64_t off)
         const uint64_t capB = std::max<uint64_t>(8, (2ull << 20) / ((s.KB + 1) * NB));
         s.slices = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(256, capA), std::max<uint64_t>(1, NB / 128));
         s.slicesB = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(256, capB), std::max<uint64_t>(1, NA / 2048));
+        if (fused_b(s)) s.slicesB = adjb_slots(s.KA - 4, nullptr);     // one partial table per (lA, column chunk)
         s.stA = take((s.KA + 1) * NA);
         s.stB = take((s.KB + 1) * NB);
         s.stP = take((uint64_t)s.slices * (s.KA + 1) * NA);
@@ -377,17 +395,21 @@ static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_da
                     for (uint32_t lb = 0; lb < nlo; ++lb) items.push_back({i, lb, hb});
             }
         ck.diag.cnt = (uint32_t)(items.size() - ck.diag.off);
-        auto blocked = [&](const SpaceDev& s) { return blocked_space(s); };
-        // generic big-tier kernel (pairs with split tables or 1-2 PT bits): segments of 32-state blocks per popcount level
+        // spaces the tiled solve kernel takes (must agree with tiled_space() on the device side)
+        auto tiled = [&](const SpaceDev& s) {
+            if (bits(s) < BIGK || s.kind == K_PRE) return false;
+            if (s.kind == K_JOINT) return !s.splitA && !s.splitB && s.KA >= 4;
+            return s.splitA >= 4;
+        };
         auto levels_of = [&](auto pred, std::vector<Range>& lv) {
             int maxkh = -1;
-            for (uint32_t i = 0; i < ck.nspaces; ++i) if (pred(sp[i]) && bits(sp[i]) >= BIGK && !blocked(sp[i])) maxkh = std::max(maxkh, bits(sp[i]) - 7);
+            for (uint32_t i = 0; i < ck.nspaces; ++i) if (pred(sp[i]) && bits(sp[i]) >= BIGK && !tiled(sp[i])) maxkh = std::max(maxkh, bits(sp[i]) - 7);
             if (maxkh < 0) return;
             lv.resize(maxkh + 1);
             for (int l = 0; l <= maxkh; ++l) {
                 lv[l].off = items.size();
                 for (uint32_t i = 0; i < ck.nspaces; ++i) {
-                    if (!pred(sp[i]) || bits(sp[i]) < BIGK || blocked(sp[i])) continue;
+                    if (!pred(sp[i]) || bits(sp[i]) < BIGK || tiled(sp[i])) continue;
                     const int kh = bits(sp[i]) - 7;          // blocks of 128 states
                     if (l > kh) continue;
                     need_hs(kh);
@@ -398,32 +420,72 @@ static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_da
                 lv[l].cnt = (uint32_t)(items.size() - lv[l].off);
             }
         };
-        // blocked kernel: one launch per level of the K-12 outer bits; an item is a run of blocks of one space, one
-        // block per warp at a time.  Thin levels get one block per warp, fat ones up to 8 rounds per CTA.
-        auto levels_of_b = [&](auto pred, std::vector<Range>& lv) {
+        // tiled kernel: rows x column blocks, one launch per level lA + lB; a CTA item is up to TILES_PER_CTA warp
+        // tiles (8 rows x 16 columns) of one (lA, lB) split
+        auto levels_of_t = [&](auto pred, std::vector<Range>& lv) {
             int maxl = -1;
+            auto dims = [&](const SpaceDev& s, int& kbA, int& kbB) {
+                if (s.kind == K_JOINT) { kbA = s.KA - 4; kbB = s.KB; }
+                else { kbA = s.splitA - 4; kbB = s.KA - s.splitA; }
+            };
             for (uint32_t i = 0; i < ck.nspaces; ++i)
-                if (pred(sp[i]) && blocked(sp[i])) maxl = std::max(maxl, bits(sp[i]) - BLK_CB - BLK_SB);
+                if (pred(sp[i]) && tiled(sp[i])) { int a, b; dims(sp[i], a, b); maxl = std::max(maxl, a + b); }
             if (maxl < 0) return;
             lv.resize(maxl + 1);
             for (int l = 0; l <= maxl; ++l) {
                 lv[l].off = items.size();
+                // thin levels: one tile per warp (the launch is a single wave and its duration the latency of the
+                // tiles a warp runs back to back); fat levels: up to TILES_PER_CTA tiles per CTA
                 uint64_t total = 0;
                 for (int pass = 0; pass < 2; ++pass) {
-                    // one block per warp on thin levels (latency), 2-4 per warp once the level is several waves deep: the
-                    // per-CTA setup and the first block's table are amortised, the next block's table is prefetched
-                    const uint64_t wave = (uint64_t)BLKW * 148;
-                    const uint32_t rounds = total <= wave ? 1u : total <= 6 * wave ? 2u : 4u;
-                    const uint32_t per_cta = rounds * BLKW;
+                    const uint64_t per_cta = total <= 8ull * 3 * 148 ? 8 : total <= 16ull * 3 * 148 ? 16 : TILES_PER_CTA;
                     for (uint32_t i = 0; i < ck.nspaces; ++i) {
-                        if (!pred(sp[i]) || !blocked(sp[i])) continue;
-                        const int ko = bits(sp[i]) - BLK_CB - BLK_SB;
-                        if (l > ko) continue;
-                        need_hs(ko);
-                        const uint32_t nblk = hs_lvl[ko][l + 1] - hs_lvl[ko][l];
-                        if (pass == 0) { total += nblk; continue; }
-                        for (uint32_t b0 = 0; b0 < nblk; b0 += per_cta)
-                            items.push_back({i, (uint32_t)l, b0, std::min<uint32_t>(per_cta, nblk - b0)});
+                        if (!pred(sp[i]) || !tiled(sp[i])) continue;
+                        int kbA, kbB;
+                        dims(sp[i], kbA, kbB);
+                        if (l > kbA + kbB) continue;
+                        need_hs(kbA); need_hs(kbB);
+                        for (int lA = std::max(0, l - kbB); lA <= std::min(kbA, l); ++lA) {
+                            const int lB = l - lA;
+                            const uint64_t nA = hs_lvl[kbA][lA + 1] - hs_lvl[kbA][lA];
+                            const uint64_t nB = hs_lvl[kbB][lB + 1] - hs_lvl[kbB][lB];
+                            const uint64_t T = nA * ((nB + 7) / 8);
+                            if (pass == 0) { total += T; continue; }
+                            for (uint64_t t0 = 0; t0 < T; t0 += per_cta)
+                                items.push_back({i, (uint32_t)lA | ((uint32_t)lB << 8) | ((uint32_t)std::min<uint64_t>(per_cta, T - t0) << 16), (uint32_t)t0});
+                        }
+                    }
+                }
+                lv[l].cnt = (uint32_t)(items.size() - lv[l].off);
+            }
+        };
+        // adjoint pass with fused group-B statistics: CTA = G row groups x C column blocks of one (lA, lB) split
+        auto levels_of_adjb = [&](std::vector<Range>& lv) {
+            int maxl = -1;
+            for (uint32_t i = 0; i < ck.nspaces; ++i)
+                if (fused_b(sp[i])) maxl = std::max(maxl, (int)sp[i].KA - 4 + (int)sp[i].KB);
+            if (maxl < 0) return;
+            lv.resize(maxl + 1);
+            for (int l = 0; l <= maxl; ++l) {
+                lv[l].off = items.size();
+                for (uint32_t i = 0; i < ck.nspaces; ++i) {
+                    if (!fused_b(sp[i])) continue;
+                    const int kbA = sp[i].KA - 4, kbB = sp[i].KB;
+                    if (l > kbA + kbB) continue;
+                    need_hs(kbA); need_hs(kbB);
+                    uint32_t base[MMH_MAX_BITS + 1];
+                    adjb_slots(kbA, base);
+                    for (int lA = std::max(0, l - kbB); lA <= std::min(kbA, l); ++lA) {
+                        const int lB = l - lA;
+                        const uint32_t nA = hs_lvl[kbA][lA + 1] - hs_lvl[kbA][lA];
+                        const uint32_t nB = hs_lvl[kbB][lB + 1] - hs_lvl[kbB][lB];
+                        const uint32_t nBg = (nB + 7) / 8;
+                        uint32_t C = 32;
+                        if (nA < 32) { C = 1; while (C < nA) C <<= 1; }
+                        const uint32_t G = 32 / C, nch = nA < 32 ? 1 : (nA + 31) / 32;
+                        for (uint32_t jB = 0; jB < nBg; jB += G)
+                            for (uint32_t k = 0; k < nch; ++k)
+                                items.push_back({i, (uint32_t)lA | ((uint32_t)lB << 8), jB, k | ((base[lA] + k) << 16)});
                     }
                 }
                 lv[l].cnt = (uint32_t)(items.size() - lv[l].off);
@@ -431,8 +493,10 @@ static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_da
         };
         levels_of(is_main, ck.main_lv);
         levels_of(is_sec, ck.sec_lv);
-        levels_of_b(is_main, ck.main_lvb);
-        levels_of_b(is_sec, ck.sec_lvb);
+        levels_of_t(is_main, ck.main_lvt);
+        levels_of_t([&](const SpaceDev& s) { return is_main(s) && !fused_b(s); }, ck.main_lvt_adj);
+        levels_of_adjb(ck.main_lvt_adjb);
+        levels_of_t(is_sec, ck.sec_lvt);
         ck.st_a.off = items.size();
         for (uint32_t i = 0; i < ck.nspaces; ++i)
             if (sp[i].kind == K_JOINT) {
@@ -452,7 +516,7 @@ static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_da
         ck.st_ar.cnt = (uint32_t)(items.size() - ck.st_ar.off);
         ck.st_b.off = items.size();
         for (uint32_t i = 0; i < ck.nspaces; ++i)
-            if (sp[i].kind == K_JOINT)
+            if (sp[i].kind == K_JOINT && !fused_b(sp[i]))
                 for (uint32_t sl = 0; sl < sp[i].slicesB; ++sl)
                     for (uint32_t u = 0; u < (1u << sp[i].KB); ++u) items.push_back({i, u, sl});
         ck.st_b.cnt = (uint32_t)(items.size() - ck.st_b.off);
@@ -534,8 +598,6 @@ static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_da
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
-    CK(cudaFuncSetAttribute(k_blk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BLK_SMEM));
-    CK(cudaFuncSetAttribute(k_blk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BLK_SMEM));
     CK(cudaFuncSetAttribute(k_finish<MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIN_SMEM));
     CK(cudaFuncSetAttribute(k_finish<MAXG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIN_SMEM));
     h->st.scratch_bytes = (double)max_scratch * 8.0 * h->ns;
@@ -605,13 +667,13 @@ static int enqueue_eval(mmh_handle* h, const double* d_params, double w0, double
                 ++launches;
             }
         };
-        auto bigb = [&](const std::vector<Range>& lv, bool adj) {
+        auto bigt = [&](const std::vector<Range>& lv, bool adj) {
             const int L = (int)lv.size();
             for (int q = 0; q < L; ++q) {
                 const Range& r = lv[adj ? L - 1 - q : q];
                 if (!r.cnt) continue;
-                if (adj) k_blk<true><<<r.cnt, BLKW * 32, BLK_SMEM, st>>>(sp, h->d_items + r.off, h->d_hs, h->d_hsidx, S);
-                else     k_blk<false><<<r.cnt, BLKW * 32, BLK_SMEM, st>>>(sp, h->d_items + r.off, h->d_hs, h->d_hsidx, S);
+                if (adj) k_solve_tile<true><<<r.cnt, 256, 0, st>>>(sp, h->d_items + r.off, h->d_hs, h->d_hsidx, S);
+                else     k_solve_tile<false><<<r.cnt, 256, 0, st>>>(sp, h->d_items + r.off, h->d_hs, h->d_hsidx, S);
                 ++launches;
             }
         };
@@ -622,15 +684,15 @@ static int enqueue_eval(mmh_handle* h, const double* d_params, double w0, double
         tick(1);
         small(ck.pre, false); small4(ck.pre4, false);
         small(ck.main_small, false); small4(ck.main_small4, false);
-        big(ck.main_lv, false); bigb(ck.main_lvb, false);
+        big(ck.main_lv, false); bigt(ck.main_lvt, false);
         small(ck.sec_small, false); small4(ck.sec_small4, false);
-        big(ck.sec_lv, false); bigb(ck.sec_lvb, false);
+        big(ck.sec_lv, false); bigt(ck.sec_lvt, false);
         tick(5);
         if (ck.logp.cnt) { k_logp<<<(ck.logp.cnt + 127) / 128, 128, 0, st>>>(sp, h->d_lists + ck.logp.off, ck.logp.cnt, S, h->d_logp); ++launches; }
         if (!want_grad) continue;
         tick(2);
         small(ck.sec_small, true); small4(ck.sec_small4, true);
-        big(ck.sec_lv, true); bigb(ck.sec_lvb, true);
+        big(ck.sec_lv, true); bigt(ck.sec_lvt, true);
         tick(5);
         if (ck.joints.cnt) {
             k_direct<<<(ck.joints.cnt + 255) / 256, 256, 0, st>>>(sp, h->d_lists + ck.joints.off, ck.joints.cnt, S, d_tdir);
@@ -639,7 +701,13 @@ static int enqueue_eval(mmh_handle* h, const double* d_params, double w0, double
         }
         tick(2);
         small(ck.main_small, true); small4(ck.main_small4, true);
-        big(ck.main_lv, true); bigb(ck.main_lvb, true);
+        big(ck.main_lv, true); bigt(ck.main_lvt_adj, true);
+        for (int q = (int)ck.main_lvt_adjb.size() - 1; q >= 0; --q) {
+            const Range& r = ck.main_lvt_adjb[q];
+            if (!r.cnt) continue;
+            k_solve_tile_adjb<<<r.cnt, 256, 0, st>>>(sp, h->d_items + r.off, h->d_hs, h->d_hsidx, S);
+            ++launches;
+        }
         small(ck.pre, true); small4(ck.pre4, true);
         tick(3);
         if (ck.st_a.cnt) {

@@ -13,8 +13,6 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
-#include "mmh_blk.cuh"
-
 namespace mmh {
 
 constexpr int NR      = 32;   // table rows per group (events 0..28, then the three special rows)
@@ -684,6 +682,69 @@ k_solve_big4(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs,
     else                for (uint32_t r = w; r < sg.b; r += nw) solve_block4<ADJ, 0>(sp, spaces, ctx, S, hs[sg.a + r], lane);
 }
 
+// ------------------------------------------------------------------------------------------
+// Tiled solve (big tier, K >= BIGK).  The lattice is viewed as rows x columns:
+//   pair            : columns = group A (KC = KA bits), rows = group B (KR = KB bits); an A-edge's rate is a column
+//                     vector T_A[ev][uA], a B-edge's rate one scalar T_B[ev][uB] per row
+//   product single  : columns = the K1 low bits, rows = the K2 high bits; every rate is a column factor T1[ev][lo]
+//                     times a row factor T2[ev][hi]
+// A warp solves 8 independent rows x 16 consecutive columns: lane = (row group, 4 columns); column bits 0,1 live in
+// the lane's registers, bits 2,3 in the four lanes of a row group (three sub-levels, 3 shuffles per state), all
+// higher bits read 128-byte lines of blocks finished by earlier launches.  The 8 rows of a tile have the same
+// popcount lB and share the column block cA (popcount lA), so every loop of the warp has a uniform trip count and
+// the column-rate loads of the 8 row groups hit the same line.  One launch per level lA + lB.
+constexpr int TILES_PER_CTA = 32;
+#ifndef TILE_CTAS
+#define TILE_CTAS 4            // resident CTAs per SM of k_solve_tile (64 registers; 3 measured 1.2 % slower)
+#endif
+#ifndef ADJB_CTAS
+#define ADJB_CTAS 3
+#endif
+#ifndef TILE_NBA
+#define TILE_NBA 2            // column-bit edges in flight per round
+#endif
+#ifndef TILE_NBB
+#define TILE_NBB 3            // row-bit edges in flight per round
+#endif
+
+struct TileCtx {
+    const double* colA[MAXG];          // column bit q: column factor of its rate (T_A[ev] or T1[ev])
+    const double* rowA[MAXG];          // product only: row factor T2[ev] of column bit q
+    const double* rowB[MAXG];          // row bit b: row factor (T_B[ev] or T2[ev])
+    const double* colB[MAXG];          // product only: column factor T1[ev] of row bit b
+    const double* dA;                  // pair: A part of the diagonal; product: the full diagonal vector
+    const double* dB;                  // pair: B part of the diagonal
+    int KC, KR;
+};
+
+__device__ __forceinline__ bool tiled_space(const SpaceDev& sp)
+{
+    if ((int)sp.KA + (int)sp.KB < BIGK || sp.kind == K_PRE) return false;
+    if (sp.kind == K_JOINT) return !sp.splitA && !sp.splitB && sp.KA >= 4;
+    return sp.splitA >= 4;
+}
+
+__device__ __forceinline__ void tile_ctx_build(TileCtx& c, const SpaceDev& sp, const double* __restrict__ S, int t)
+{
+    if (sp.kind == K_JOINT) {
+        const int KA = sp.KA, KB = sp.KB;
+        if (t < KA) { c.colA[t] = S + sp.tabA + ((uint64_t)sp.evA[t] << KA); c.rowA[t] = &c_one; }
+        if (t < KB) { c.rowB[t] = S + sp.tabB + ((uint64_t)sp.evB[t] << KB); c.colB[t] = &c_one; }
+        if (t == 0) {
+            c.dA = S + sp.tabA + ((uint64_t)ROW_D << KA);
+            c.dB = S + sp.tabB + ((uint64_t)ROW_D << KB);
+            c.KC = KA; c.KR = KB;
+        }
+    } else {
+        const int K1 = sp.splitA, K2 = sp.KA - K1;
+        const double* T1 = S + sp.tabA;
+        const double* T2 = T1 + ((uint64_t)NR << K1);
+        if (t < K1) { c.colA[t] = T1 + ((uint64_t)sp.evA[t] << K1); c.rowA[t] = T2 + ((uint64_t)sp.evA[t] << K2); }
+        if (t < K2) { c.rowB[t] = T2 + ((uint64_t)sp.evA[K1 + t] << K2); c.colB[t] = T1 + ((uint64_t)sp.evA[K1 + t] << K1); }
+        if (t == 0) { c.dA = T2 + ((uint64_t)NR << K2); c.dB = &c_zero; c.KC = K1; c.KR = K2; }
+    }
+}
+
 // 32-byte global load / store (LDG.E.256 / STG.E.256 on sm_100a): four lanes cover one 128-byte line with a single
 // request, which halves the L1 wavefronts of the tile kernels against two 16-byte loads per lane.
 __device__ __forceinline__ void ld4(const double* __restrict__ p, double (&f)[4])
@@ -695,239 +756,374 @@ __device__ __forceinline__ void st4(double* __restrict__ p, double a, double b, 
     asm volatile("st.global.v4.f64 [%4], {%0,%1,%2,%3};" :: "d"(a), "d"(b), "d"(c), "d"(d), "l"(p) : "memory");
 }
 
-// ------------------------------------------------------------------------------------------
-// Big tier (K >= BIGK): blocked substitution, one warp per 2^12-state block kept in shared memory, launches level by
-// level over the popcount of the K-12 outer bits (mmh_blk.cuh has the algorithm; this is the adapter from a space's
-// tables to its abstract description and the kernel around it).
-//   pair (no split tables, KA >= 3 or KA == 0): an A-bit's rate is the vector T_A[ev][uA], a B-bit's rate the scalar
-//       T_B[ev][uB]; diag = D_A[uA] + D_B[uB]
-//   single-tumour space in product form with K1 = 8: rate = T1[ev][u & 255] * T2[ev][u >> 8], full diagonal vector
-constexpr int BLKW = 4;                                  // warps (= blocks in flight) per CTA
-// per warp: the block (32 KB) + the ring of source rows (10 KB) + the per-row scalars of this and the next block (2 x 3 KB);
-// per CTA: the column profiles (30 KB)
-constexpr int BLK_WARP_DOUBLES = BLK_DOUBLES + BLK_NS * BLK_ROW + 2 * BLK_SC_DOUBLES;
-constexpr int BLK_CTA_DOUBLES = BLKW * BLK_WARP_DOUBLES + BLK_MAXC * BLK_ROW;
-
-__host__ __device__ __forceinline__ bool blocked_space(const SpaceDev& sp)
-{
-    const int K = (int)sp.KA + (int)sp.KB;
-    if (K < BIGK || sp.kind == K_PRE) return false;
-    if (K - BLK_CB - BLK_SB > BLK_MAXKO) return false;
-    if (sp.kind == K_JOINT) return !sp.splitA && !sp.splitB;
-    return sp.splitA == BLK_CB && K - BLK_CB <= BLK_MAXC;      // one column profile per non-column bit
-}
-
-__device__ __forceinline__ void blk_ctx_build(BlkCtx& c, const SpaceDev& sp, const double* __restrict__ S, int tid)
-{
-    const int KA = sp.KA, KB = sp.KB, K = KA + KB;
-    const bool joint = sp.kind == K_JOINT;
-    if (tid < K) {
-        BlkBit b;
-        b.cidx = -1;
-        if (joint) {
-            if (tid < KA) { b.P = S + sp.tabA + ((uint64_t)sp.evA[tid] << KA); b.mP = (1u << KA) - 1u; b.Q = nullptr; b.mQ = 0; b.shQ = BLK_CB; }
-            else if (KA == 0) { b.P = S + sp.tabB + ((uint64_t)sp.evB[tid] << KB); b.mP = (1u << KB) - 1u; b.Q = nullptr; b.mQ = 0; b.shQ = BLK_CB; }
-            else { b.P = nullptr; b.mP = 1u; b.Q = S + sp.tabB + ((uint64_t)sp.evB[tid - KA] << KB); b.mQ = (1u << KB) - 1u; b.shQ = (uint32_t)KA; }
-        } else {
-            const int K2 = K - BLK_CB;
-            const double* T1 = S + sp.tabA;
-            const double* T2 = T1 + ((uint64_t)NR << BLK_CB);
-            b.P = T1 + ((uint64_t)sp.evA[tid] << BLK_CB); b.mP = (1u << BLK_CB) - 1u;
-            b.Q = T2 + ((uint64_t)sp.evA[tid] << K2); b.mQ = (1u << K2) - 1u; b.shQ = BLK_CB;
-        }
-        c.bit[tid] = b;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        if (joint) {
-            const double* dA = S + sp.tabA + ((uint64_t)ROW_D << KA);
-            const double* dB = S + sp.tabB + ((uint64_t)ROW_D << KB);
-            if (KA == 0) { c.d1 = dB; c.m1 = (1u << KB) - 1u; c.d2 = dA; c.m2 = 0; c.sh2 = BLK_CB; }
-            else { c.d1 = dA; c.m1 = (1u << KA) - 1u; c.d2 = dB; c.m2 = (1u << KB) - 1u; c.sh2 = (uint32_t)KA; }
-        } else {
-            const int K2 = K - BLK_CB;
-            c.d1 = S + sp.tabA + ((uint64_t)NR << BLK_CB) + ((uint64_t)NR << K2);
-            c.m1 = (1u << K) - 1u; c.d2 = nullptr; c.m2 = 0; c.sh2 = BLK_CB;
-        }
-        blk_ctx_layout(c, K, (joint && KA > BLK_CB) ? KA : BLK_CB);
-    }
-    __syncthreads();
-}
-
-// right-hand side of the eight states s0 + blk_joff(j) of a lane: non-zero on few lanes only (except the second phase's
-// start vector), so a cheap necessary condition on the lane's states comes first
+// right-hand side of the four states of a lane: non-zero on few states only (except the second phase's start vector)
 template <bool ADJ>
-struct BlkRhs {
-    const SpaceDev& sp;
-    const SpaceDev* __restrict__ spaces;
-    const double* __restrict__ S;
-    __device__ __forceinline__ void operator()(uint32_t s0, double (&acc)[8]) const
+__device__ __forceinline__ void tile_rhs(const SpaceDev& sp, const SpaceDev* __restrict__ spaces, const double* __restrict__ S,
+                                         int KC, int KR, uint32_t row, uint32_t lo0, double (&acc)[4])
+{
+    const uint32_t s0 = (row << KC) | lo0;
     {
-        const int KA = sp.KA, KB = sp.KB;
-        const uint32_t NA = 1u << KA, NB = 1u << KB;
-        const uint32_t hi = s0 | BLK_REGMASK;                        // the lane's states lie between s0 and hi, bitwise
+        const uint32_t NC = 1u << KC, NRW = 1u << KR;
         bool any;
         if (!ADJ) {
-            if (sp.kind == K_JOINT) any = (s0 >> KA) < (1u << sp.nb);   // seeding inflow: rows uB < 2^nb only
+            if (sp.kind == K_JOINT) any = row < (1u << sp.nb) && ((row ^ lo0) & ~3u) == 0u;
             else if (sp.kind == K_PF || sp.kind == K_MF) any = true;
-            else any = (s0 & ~BLK_REGMASK) == 0u;
+            else any = s0 == 0u;
         } else {
-            if (sp.kind == K_JOINT) any = (sp.has_pf && (hi & (NA - 1u)) == NA - 1u) || (sp.has_mf && (hi >> KA) == NB - 1u);
-            else any = hi == (NA << KB) - 1u;
+            if (sp.kind == K_JOINT) any = (sp.has_pf && (lo0 | 3u) == NC - 1u) || (sp.has_mf && row == NRW - 1u);
+            else any = (s0 | 3u) == (NC << KR) - 1u;
         }
         if (any) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint32_t s = s0 + blk_joff(j);
-                acc[j] = ADJ ? rhs_adj(sp, spaces, S, s) : rhs_fwd(sp, spaces, S, s);
-            }
+            for (int t = 0; t < 4; ++t) acc[t] = ADJ ? rhs_adj(sp, spaces, S, s0 + t) : rhs_fwd(sp, spaces, S, s0 + t);
         }
     }
-};
-
-// ---- bulk asynchronous copy (TMA) + mbarrier, the subset this kernel needs ----
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "MBAR_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra MBAR_DONE;\n"
-        "bra MBAR_WAIT;\n"
-        "MBAR_DONE:\n"
-        "}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// the block loop of one warp (SIMPLE: the instantiation without column profiles on the sequence bits, see BlkCtx::simple)
-template <bool ADJ, bool SIMPLE>
-__device__ __forceinline__ void blk_run(const BlkCtx& ctx, BlkPlan* plan2, uint64_t* bar, double* sm, const double* ctab,
-                                        double* __restrict__ v, const BlkRhs<ADJ>& rhs, const uint32_t* __restrict__ olist,
-                                        uint32_t count, int lane, int w)
+// edges on the row bits of a lane's four states (sources in global memory): acc += rate * v[other row]
+template <bool ADJ, bool PROD>
+__device__ __forceinline__ void tile_row_edges(const TileCtx& c, const double* __restrict__ v, uint32_t row, uint32_t lo0,
+                                               double (&acc)[4])
 {
-    double* ring = sm + BLK_DOUBLES;
-    double* sc2 = ring + BLK_NS * BLK_ROW;
-    BlkLane L;
-    blk_lane_consts<ADJ>(ctx, lane, L);                   // column-bit rate profiles of the lane's states: once per CTA
-    for (int i = lane * 2; i < BLK_DOUBLES; i += 64) *reinterpret_cast<double2*>(sm + i) = make_double2(0.0, 0.0);
-    uint32_t slot = 0, par = 0;                           // ring position of the next source row to consume (runs over the blocks)
-    int cur = 0;
-    if ((uint32_t)w < count) {                            // table of the first block: computed in place
-        if (lane == 0) blk_plan(ctx, olist[w], ADJ, plan2[0]);
-        __syncwarp();
-        for (int i = lane; i < BLK_Q * (BLK_SC_OUT + plan2[0].nE); i += 32) blk_sc_entry<ADJ>(ctx, plan2[0], i, sc2);
-    }
-    __syncwarp();
-    for (uint32_t k = w; k < count; k += BLKW) {
-        const BlkPlan& plan = plan2[cur];
-        const double* sc = sc2 + cur * BLK_SC_DOUBLES;
-        double* sc_next = sc2 + (cur ^ 1) * BLK_SC_DOUBLES;
-        const bool has_next = k + BLKW < count;
-        const uint32_t o_next = has_next ? olist[k + BLKW] : 0u;
-        const int nE = plan.nE;
-        const uint32_t total = (uint32_t)BLK_Q * nE;
-        // producer state (lane 0 issues; every lane tracks it): next source row = (i_row, i_k), into ring slot i_slot
-        uint32_t issued = 0, i_row = 0, i_slot = slot;
-        int i_k = 0;
-        auto issue = [&]() {
-            if (lane == 0) {
-                const uint32_t src = blk_chunk_row<ADJ>(ctx, plan, i_row, i_k);
-                mbar_expect_tx(&bar[i_slot], BLK_ROW * sizeof(double));
-                bulk_g2s(ring + i_slot * BLK_ROW, v + src, BLK_ROW * sizeof(double), &bar[i_slot]);
-            }
-            ++issued;
-            if (++i_k == nE) { i_k = 0; ++i_row; }
-            if (++i_slot == BLK_NS) i_slot = 0;
-        };
-        while (issued < total && issued < (uint32_t)BLK_NS) issue();
-        blk_lane_block(ctx, plan.base, lane, L);
-#pragma unroll 1
-        for (int t = 0; t < BLK_ITERS; ++t) {
-            // the NEXT block's table of per-row scalars is computed while this block runs: the loads of one entry per lane
-            // are issued here and stored at the end of the iteration
-            BlkScReq rq{nullptr, nullptr, -1};
-            double va = 1.0, vb = 1.0;
-            if (has_next) {
-                if (t == 0) { if (lane == 0) blk_plan(ctx, o_next, ADJ, plan2[cur ^ 1]); }
-                else {
-                    rq = blk_sc_request<ADJ>(ctx, plan2[cur ^ 1], (t - 1) * 32 + lane);
-                    if (rq.a) va = *rq.a;
-                    if (rq.b) vb = *rq.b;
-                }
-            }
-            if (t < BLK_Q) {
-                // ---- OUTER phase: all lanes on the row of this iteration ----
-                const uint32_t q = ADJ ? (uint32_t)(BLK_Q - 1 - t) : (uint32_t)t;
-                const uint32_t s0 = L.base | blk_seq_mask(ctx, q);
-                double acc[8];
+    const int KC = c.KC, KR = c.KR;
+    {
+        constexpr int NB = TILE_NBB;
+        uint32_t m = ADJ ? (~row & ((1u << KR) - 1u)) : row;
+        while (m) {
+            double y[NB][4], k[NB];
+            int bq[NB];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = 0.0;
-                rhs(s0, acc);
-                const double* scq = sc + q * BLK_SCW + BLK_SC_OUT;
-#pragma unroll 1
-                for (int e = 0; e < nE; ++e) {
-                    const int ci = plan.ecidx[e];
-                    mbar_wait(&bar[slot], par);
-                    blk_outer_edge(lane, scq[e], ci >= 0 ? ctab + ci * BLK_ROW : nullptr, ring + slot * BLK_ROW, acc);
-                    if (++slot == BLK_NS) { slot = 0; par ^= 1u; }
-                    __syncwarp();                    // every lane has read the slot: it can be refilled
-                    if (issued < total) issue();
+            for (int q = 0; q < NB; ++q) {
+                const bool on = m != 0u;
+                const int b = on ? __ffs(m) - 1 : 0;
+                m &= m - 1;
+                bq[q] = b;
+                const uint32_t orow = row ^ (1u << b);
+                if (on) {
+                    k[q] = c.rowB[b][ADJ ? row : orow];
+                    ld4(v + (((uint64_t)orow << KC) | lo0), y[q]);
+                } else {
+                    k[q] = 0.0;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) y[q][t] = 0.0;
                 }
-                blk_sts8(sm + q * BLK_ROW + lane * 2, acc);
             }
-            // ---- INNER phase: skewed wavefront ----
-            blk_inner<ADJ, SIMPLE>(ctx, L, lane, t, v, sm, sm, sc, ctab);
-            blk_sc_store(rq, va, vb, sc_next);
-            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+                if (PROD) {
+                    double cf[4];
+                    ld4(c.colB[bq[q]] + lo0, cf);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) acc[t] = fma(cf[t] * k[q], y[q][t], acc[t]);
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) acc[t] = fma(k[q], y[q][t], acc[t]);
+                }
+            }
         }
-        cur ^= 1;
     }
 }
 
-// item: space, a = outer level, b = first block of that level (index into the popcount-sorted list), c = blocks
-template <bool ADJ>
-__global__ void __launch_bounds__(BLKW * 32, 1)
-k_blk(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, const uint32_t* __restrict__ hs,
-      const uint32_t* __restrict__ hsidx, double* __restrict__ S)
+// diagonal, column bits 0,1 (inside the lane) and 2,3 (across the four lanes of a row group): acc -> val
+template <bool ADJ, bool PROD>
+__device__ __forceinline__ void tile_tail(const TileCtx& c, uint32_t row, uint32_t lo0, int lane, double (&acc)[4], double (&val)[4])
 {
-    extern __shared__ __align__(128) double blk_sm[];
-    __shared__ BlkCtx ctx;
-    __shared__ BlkPlan plans[BLKW][2];
-    __shared__ __align__(8) uint64_t bars[BLKW][BLK_NS];
-    const Item it = items[blockIdx.x];
-    const SpaceDev& sp = spaces[it.space];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) {
-        for (int s = 0; s < BLK_NS; ++s) mbar_init(&bars[w][s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const int KC = c.KC;
+    const int lc = lane & 3;
+    const uint32_t s0 = (row << KC) | lo0;
+    // ---- diagonal ----
+    double inv[4];
+    {
+        double d[4];
+        if (PROD) ld4(c.dA + s0, d);
+        else {
+            ld4(c.dA + lo0, d);
+            const double k = c.dB[row];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) d[t] += k;
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) inv[t] = 1.0 / d[t];
     }
-    blk_ctx_build(ctx, sp, S, threadIdx.x);          // ends with __syncthreads: the barriers are initialised for everybody
-    double* ctab = blk_sm + BLKW * BLK_WARP_DOUBLES;
-    for (int i = threadIdx.x; i < ctx.nC * BLK_ROW; i += BLKW * 32) blk_ctab_entry(ctx, ctx.cbit[i >> BLK_CB], i & (BLK_ROW - 1), ctab);
-    __syncthreads();
+    // ---- column bits 0,1 (inside the lane) and 2,3 (across the four lanes of the row group) ----
+    double k0 = 1.0, k1 = 1.0, k2 = 1.0, k3 = 1.0;
+    if (PROD) { k0 = c.rowA[0][row]; k1 = c.rowA[1][row]; k2 = c.rowA[2][row]; k3 = c.rowA[3][row]; }
+    double e0a, e0b, e1a, e1b;
+    {
+        double q0[4], q1[4];
+        ld4(c.colA[0] + lo0, q0);
+        ld4(c.colA[1] + lo0, q1);
+        e0a = q0[0] * k0; e0b = q0[2] * k0;          // bit 0: 0 -> 1, 2 -> 3
+        e1a = q1[0] * k1; e1b = q1[1] * k1;          // bit 1: 0 -> 2, 1 -> 3
+    }
+    double w0[4] = {0.0, 0.0, 0.0, 0.0}, w1a[4] = {0.0, 0.0, 0.0, 0.0}, w1b[4] = {0.0, 0.0, 0.0, 0.0};
+    const int pl = __popc(lc);
+    if (!ADJ) {
+        // round 0: lanes 1, 2 receive from lane 0;  round 1: lane 3 receives from lanes 2 (bit 2) and 1 (bit 3)
+        if (pl == 1) {
+            const int q = lc == 2;
+            ld4(c.colA[2 + q] + (lo0 ^ (4u << q)), w0);
+            const double k = q ? k3 : k2;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) w0[t] *= k;
+        } else if (lc == 3) {
+            ld4(c.colA[2] + (lo0 ^ 4u), w1a);
+            ld4(c.colA[3] + (lo0 ^ 8u), w1b);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { w1a[t] *= k2; w1b[t] *= k3; }
+        }
+    } else {
+        // round 0: lanes 1, 2 receive from lane 3;  round 1: lane 0 receives from lanes 1 (bit 2) and 2 (bit 3)
+        if (pl == 1) {
+            const int q = lc == 1;                   // the bit this lane lacks
+            ld4(c.colA[2 + q] + lo0, w0);
+            const double k = q ? k3 : k2;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) w0[t] *= k;
+        } else if (lc == 0) {
+            ld4(c.colA[2] + lo0, w1a);
+            ld4(c.colA[3] + lo0, w1b);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { w1a[t] *= k2; w1b[t] *= k3; }
+        }
+    }
+    auto fin = [&]() {
+        if (!ADJ) {
+            val[0] = acc[0] * inv[0];
+            val[1] = fma(e0a, val[0], acc[1]) * inv[1];
+            val[2] = fma(e1a, val[0], acc[2]) * inv[2];
+            val[3] = fma(e0b, val[2], fma(e1b, val[1], acc[3])) * inv[3];
+        } else {
+            val[3] = acc[3] * inv[3];
+            val[2] = fma(e0b, val[3], acc[2]) * inv[2];
+            val[1] = fma(e1b, val[3], acc[1]) * inv[1];
+            val[0] = fma(e0a, val[1], fma(e1a, val[2], acc[0])) * inv[0];
+        }
+    };
+    // Values of lanes that are not final yet are finite partial results and only ever meet a zero weight.
+    fin();
+    {
+        const int src = ADJ ? (lane | 3) : (lane & ~3);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) acc[t] = fma(w0[t], __shfl_sync(0xffffffffu, val[t], src), acc[t]);
+    }
+    fin();
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const double p = __shfl_xor_sync(0xffffffffu, val[t], 1);
+        const double q = __shfl_xor_sync(0xffffffffu, val[t], 2);
+        acc[t] = fma(w1b[t], q, fma(w1a[t], p, acc[t]));
+    }
+    fin();
+}
+
+template <bool ADJ, bool PROD>
+__device__ __forceinline__ void solve_tile16(const SpaceDev& sp, const SpaceDev* __restrict__ spaces, const TileCtx& c,
+                                             double* __restrict__ S, uint32_t cA, uint32_t row, bool valid, int lane)
+{
+    const int KC = c.KC, KR = c.KR;
+    const int lc = lane & 3;
+    const uint32_t lo0 = (cA << 4) | ((uint32_t)lc << 2);
+    const uint32_t s0 = (row << KC) | lo0;
     double* v = S + (ADJ ? sp.x_off : sp.y_off);
-    const uint32_t* olist = hs + hsidx[ctx.KO * 32 + it.a] + it.b;
-    const BlkRhs<ADJ> rhs{sp, spaces, S};
-    double* sm = blk_sm + w * BLK_WARP_DOUBLES;
-    if (ctx.simple) blk_run<ADJ, true>(ctx, plans[w], bars[w], sm, ctab, v, rhs, olist, it.c, lane, w);
-    else            blk_run<ADJ, false>(ctx, plans[w], bars[w], sm, ctab, v, rhs, olist, it.c, lane, w);
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    tile_rhs<ADJ>(sp, spaces, S, KC, KR, row, lo0, acc);
+    // Edges are taken NB at a time, all loads of a round before its FMAs: a tile is a chain of dependent rounds and
+    // thin levels have no other warps to hide the memory latency behind.
+    // ---- column bits >= 4 (uniform over the warp): FWD visits the set bits of cA, ADJ the unset ones ----
+    {
+        constexpr int NB = TILE_NBA;
+        uint32_t m = ADJ ? (~cA & ((1u << (KC - 4)) - 1u)) : cA;
+        while (m) {
+            double r[NB][4], y[NB][4], k[NB];
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+                const bool on = m != 0u;
+                const int a = on ? __ffs(m) + 3 : 4;
+                m &= m - 1;
+                const uint32_t bit = 1u << a;
+                k[q] = 1.0;
+                if (on) {
+                    ld4(c.colA[a] + (ADJ ? lo0 : (lo0 ^ bit)), r[q]);
+                    ld4(v + (s0 ^ bit), y[q]);
+                    if (PROD) k[q] = c.rowA[a][row];
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) { r[q][t] = 0.0; y[q][t] = 0.0; }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < NB; ++q)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) acc[t] = fma(PROD ? r[q][t] * k[q] : r[q][t], y[q][t], acc[t]);
+        }
+    }
+    tile_row_edges<ADJ, PROD>(c, v, row, lo0, acc);
+    double val[4];
+    tile_tail<ADJ, PROD>(c, row, lo0, lane, acc, val);
+    if (valid) st4(v + s0, val[0], val[1], val[2], val[3]);
+}
+
+// item: space, a = lA | lB << 8 | tiles << 16, b = first tile; tile t -> column block t / nBg, row group t % nBg
+template <bool ADJ>
+__global__ void __launch_bounds__(256, TILE_CTAS)
+k_solve_tile(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs, const uint32_t* __restrict__ hs,
+             const uint32_t* __restrict__ hsidx, double* __restrict__ S)
+{
+    __shared__ TileCtx ctx;
+    const Item sg = segs[blockIdx.x];
+    const SpaceDev& sp = spaces[sg.space];
+    tile_ctx_build(ctx, sp, S, threadIdx.x);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t lA = sg.a & 255u, lB = (sg.a >> 8) & 255u, cnt = sg.a >> 16;
+    const uint32_t offA = hsidx[(ctx.KC - 4) * 32 + lA];
+    const uint32_t offB = hsidx[ctx.KR * 32 + lB];
+    const uint32_t nB = hsidx[ctx.KR * 32 + lB + 1] - offB;
+    const uint32_t nBg = (nB + 7u) >> 3;
+    const bool prod = sp.kind != K_JOINT;
+    for (uint32_t q = w; q < cnt; q += 8) {
+        const uint32_t t = sg.b + q;
+        const uint32_t iA = t / nBg, jB = t - iA * nBg;
+        const uint32_t ri = jB * 8u + (uint32_t)(lane >> 2);
+        const bool valid = ri < nB;
+        const uint32_t cA = hs[offA + iA];
+        const uint32_t row = hs[offB + min(ri, nB - 1u)];
+        if (prod) solve_tile16<ADJ, true>(sp, spaces, ctx, S, cA, row, valid, lane);
+        else      solve_tile16<ADJ, false>(sp, spaces, ctx, S, cA, row, valid, lane);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
+// Adjoint tile solve of a pair with the group-B marginal statistics fused in.  The adjoint pass already holds, for
+// every state s and every row bit b not in s, the value x[s + b]; with y[s] (one more 32-byte load) the lane adds
+//     stB[1+b][uB] += sum_uA y[s] x[s + b]      stB[0][uB] += sum_uA x[s] y[s]
+// which saves the separate k_stats_b pass (one more full read of x and y plus KB/2 re-reads of x through L2).
+// A CTA is G row groups x C column blocks (G C <= 32) of one (lA, lB) split: the per-tile sums are parked in shared
+// memory, added over the CTA's column blocks in a fixed order and written to the partial table `slot` of the space
+// (every row receives every slot exactly once, no atomics; k_stats_reduce adds the slots).
+// item: a = lA | lB << 8, b = first row group, c = column chunk k | slot << 16
+constexpr int ADJB_MAXE = 17;                       // g + up to 16 row bits (pairs with plain tables have KB <= MAXT)
+
+__device__ __forceinline__ double group4_sum(double v)
+{
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+}
+
+__global__ void __launch_bounds__(256, ADJB_CTAS)
+k_solve_tile_adjb(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs, const uint32_t* __restrict__ hs,
+                  const uint32_t* __restrict__ hsidx, double* __restrict__ S)
+{
+    __shared__ TileCtx ctx;
+    __shared__ double pb[32][8][ADJB_MAXE];
+    const Item sg = segs[blockIdx.x];
+    const SpaceDev& sp = spaces[sg.space];
+    tile_ctx_build(ctx, sp, S, threadIdx.x);
+    for (int t = threadIdx.x; t < 32 * 8 * ADJB_MAXE; t += blockDim.x) (&pb[0][0][0])[t] = 0.0;
+    __syncthreads();
+    const TileCtx& c = ctx;
+    const int KC = c.KC, KR = c.KR;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, lc = lane & 3, lg = lane >> 2;
+    const uint32_t lA = sg.a & 255u, lB = (sg.a >> 8) & 255u;
+    const uint32_t kch = sg.c & 0xffffu, slot = sg.c >> 16;
+    const uint32_t offA = hsidx[(KC - 4) * 32 + lA], nA = hsidx[(KC - 4) * 32 + lA + 1] - offA;
+    const uint32_t offB = hsidx[KR * 32 + lB], nB = hsidx[KR * 32 + lB + 1] - offB;
+    const uint32_t nBg = (nB + 7u) >> 3;
+    uint32_t C = 32;                                   // column blocks per row group in this CTA
+    if (nA < 32u) { C = 1; while (C < nA) C <<= 1; }
+    const uint32_t G = 32u / C;
+    double* v = S + sp.x_off;
+    const double* yv = S + sp.y_off;
+    for (uint32_t q = w; q < 32u; q += 8) {
+        const uint32_t g = q / C, ci = q - g * C;
+        const uint32_t jB = sg.b + g, iA = kch * 32u + ci;
+        if (jB >= nBg || iA >= nA) continue;           // uniform over the warp
+        const uint32_t ri = jB * 8u + (uint32_t)lg;
+        const bool valid = ri < nB;
+        const uint32_t cA = hs[offA + iA];
+        const uint32_t row = hs[offB + min(ri, nB - 1u)];
+        const uint32_t lo0 = (cA << 4) | ((uint32_t)lc << 2);
+        const uint32_t s0 = (row << KC) | lo0;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0}, y4[4];
+        ld4(yv + s0, y4);
+        tile_rhs<true>(sp, spaces, S, KC, KR, row, lo0, acc);
+        // column bits >= 4
+        {
+            constexpr int NB = TILE_NBA;
+            uint32_t m = ~cA & ((1u << (KC - 4)) - 1u);
+            while (m) {
+                double r[NB][4], y[NB][4];
+#pragma unroll
+                for (int e = 0; e < NB; ++e) {
+                    const bool on = m != 0u;
+                    const int a = on ? __ffs(m) + 3 : 4;
+                    m &= m - 1;
+                    if (on) { ld4(c.colA[a] + lo0, r[e]); ld4(v + (s0 | (1u << a)), y[e]); }
+                    else {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) { r[e][t] = 0.0; y[e][t] = 0.0; }
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < NB; ++e)
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) acc[t] = fma(r[e][t], y[e][t], acc[t]);
+            }
+        }
+        // row bits: solve edge and statistic from the same loaded values
+        {
+            constexpr int NB = TILE_NBB;
+            uint32_t m = ~row & ((1u << KR) - 1u);
+            while (m) {
+                double y[NB][4], k[NB];
+                int bq[NB];
+#pragma unroll
+                for (int e = 0; e < NB; ++e) {
+                    const bool on = m != 0u;
+                    const int b = on ? __ffs(m) - 1 : 0;
+                    m &= m - 1;
+                    bq[e] = on ? b : -1;
+                    if (on) {
+                        k[e] = c.rowB[b][row];
+                        ld4(v + (((uint64_t)(row | (1u << b)) << KC) | lo0), y[e]);
+                    } else {
+                        k[e] = 0.0;
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) y[e][t] = 0.0;
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < NB; ++e) {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) acc[t] = fma(k[e], y[e][t], acc[t]);
+                    const double d = group4_sum(fma(y4[3], y[e][3], fma(y4[2], y[e][2], fma(y4[1], y[e][1], y4[0] * y[e][0]))));
+                    if (lc == 0 && bq[e] >= 0) pb[q][lg][1 + bq[e]] = d;
+                }
+            }
+        }
+        double val[4];
+        tile_tail<true, false>(c, row, lo0, lane, acc, val);
+        const double gsum = group4_sum(fma(y4[3], val[3], fma(y4[2], val[2], fma(y4[1], val[1], y4[0] * val[0]))));
+        if (lc == 0) pb[q][lg][0] = gsum;
+        if (valid) st4(v + s0, val[0], val[1], val[2], val[3]);
+    }
+    __syncthreads();
+    // add the CTA's column blocks (fixed order) and write the partial table of this slot
+    const uint32_t NBr = 1u << KR;
+    double* out = S + sp.stPB + (uint64_t)slot * (KR + 1) * NBr;
+    for (uint32_t t = threadIdx.x; t < G * 8u * (uint32_t)(KR + 1); t += blockDim.x) {
+        const uint32_t e = t % (uint32_t)(KR + 1), rr = (t / (uint32_t)(KR + 1)) & 7u, g = t / ((uint32_t)(KR + 1) * 8u);
+        const uint32_t jB = sg.b + g;
+        const uint32_t ri = jB * 8u + rr;
+        if (jB >= nBg || ri >= nB) continue;
+        double s = 0.0;
+        for (uint32_t ci = 0; ci < C; ++ci) s += pb[g * C + ci][rr][e];
+        out[(uint64_t)e * NBr + hs[offB + ri]] = s;
+    }
+}
+
 __global__ void k_logp(const SpaceDev* __restrict__ spaces, const uint32_t* __restrict__ list, uint32_t count,
                        const double* __restrict__ S, double* __restrict__ logp)
 {

@@ -8,7 +8,7 @@
 #include <random>
 #include <vector>
 
-#include "../../metmhn_b200/csrc/mmh_blk.cuh"
+#include "mmh_blk.cuh"
 
 using namespace mmh;
 
@@ -218,7 +218,7 @@ int main()
         const double ef = max_rel(emulate<false>(sp), reference(sp, false));
         const double ea = max_rel(emulate<true>(sp), reference(sp, true));
         std::printf("K=%d kind=%d KA=%d simple=%d seq=[%d %d %d %d] nC=%d d1row=%d d2mode=%d  fwd %.2e  adj %.2e\n", cs.K, cs.kind, cs.KA,
-                    sp.ctx.simple, sp.ctx.seq[0], sp.ctx.seq[1], sp.ctx.seq[2], sp.ctx.seq[3], sp.ctx.nC, sp.ctx.d1row, sp.ctx.d2mode, ef, ea);
+                    sp.ctx.simple, sp.ctx.seq[0], sp.ctx.seq[1], sp.ctx.seq[2], BLK_SB > 3 ? sp.ctx.seq[BLK_SB - 1] : -1, sp.ctx.nC, sp.ctx.d1row, sp.ctx.d2mode, ef, ea);
         if (!(ef < 1e-12) || !(ea < 1e-12)) ++bad;
     }
     std::printf(bad ? "FAILED %d\n" : "OK\n", bad);

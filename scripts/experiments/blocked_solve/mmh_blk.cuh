@@ -43,18 +43,18 @@ namespace mmh {
 
 constexpr int BLK_MAXBITS = 26;
 constexpr int BLK_CB = 8;                       // column bits
-constexpr int BLK_SB = 4;                       // sequence bits
+constexpr int BLK_SB = 3;                       // sequence bits
 constexpr int BLK_Q = 1 << BLK_SB;              // rows of a block
 constexpr int BLK_ROW = 1 << BLK_CB;            // doubles per row
 constexpr int BLK_DOUBLES = BLK_Q * BLK_ROW;    // 4096 doubles = 32 KB per warp
 constexpr int BLK_ITERS = BLK_Q + 5;            // skew: 5 fill / drain iterations
-constexpr int BLK_NS = 5;                       // ring slots (one source row = 2 KB each)
+constexpr int BLK_NS = 4;                       // ring slots (one source row = 2 KB each)
 constexpr uint32_t BLK_REGMASK = 0xC1u;         // register bits of a lane's eight states: positions 0, 6, 7
 constexpr int BLK_MAXC = 15;                    // column-profile vectors of a space (256 doubles each, shared by the CTA)
-constexpr int BLK_MAXKO = 11;                   // outer bits (K <= 23)
-// per-row scalars of a block: [0..7] column-bit edges, [8..11] sequence-bit edges, [12] diagonal part, [13..] outer edges
-constexpr int BLK_SCW = 13 + BLK_MAXKO;
-constexpr int BLK_SC_SEQ = 8, BLK_SC_D2 = 12, BLK_SC_OUT = 13;
+constexpr int BLK_MAXKO = 23 - BLK_CB - BLK_SB; // outer bits (K <= 23)
+// per-row scalars of a block: [0..7] column-bit edges, then the sequence-bit edges, the diagonal part, the outer edges
+constexpr int BLK_SC_SEQ = BLK_CB, BLK_SC_D2 = BLK_CB + BLK_SB, BLK_SC_OUT = BLK_CB + BLK_SB + 1;
+constexpr int BLK_SCW = BLK_SC_OUT + BLK_MAXKO;
 constexpr int BLK_SC_DOUBLES = BLK_Q * BLK_SCW;
 
 // Edge u -> u | (1 << t) of bit t (t not in u):  rate_t(u) = P[u & mP] * Q[(u >> shQ) & mQ]   (null pointer = 1).
