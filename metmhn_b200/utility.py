@@ -118,3 +118,25 @@ def read_events_csv(events_csv: str, annot_csv: str):
     dat = np.concatenate([geno, seeding[:, None], order[keep].astype(np.int8)[:, None], t[:, None]], axis=1)
     names = [c.split(".", 1)[1] for c in muts[::2]] + ["Seeding"]
     return np.ascontiguousarray(dat.astype(np.int8)), names
+
+
+def write_model_csv(path: str, theta, d_p, d_m, events):
+    """Write a fitted model the way `examples/analysis.py:115-120` does: a pandas CSV whose columns are the event names
+    (seeding last) and whose rows are `row_stack(d_p, d_m, theta)`, indexed 0 ... n+2 (the layout of
+    `results/luad/luad_g14_20muts.csv`)."""
+    import pandas as pd
+    theta = np.asarray(theta, dtype=np.float64)
+    n_tot = theta.shape[0]
+    if theta.shape != (n_tot, n_tot) or len(events) != n_tot:
+        raise ValueError("theta must be (n+1, n+1) and `events` must name its n+1 columns (seeding last)")
+    table = np.vstack([np.asarray(d_p, dtype=np.float64).reshape(1, -1), np.asarray(d_m, dtype=np.float64).reshape(1, -1), theta])
+    pd.DataFrame(table, columns=list(events)).to_csv(path)
+
+
+def read_model_csv(path: str):
+    """Inverse of `write_model_csv`; also reads the reference's published models (`results/luad/*.csv`).
+    Returns (theta, d_p, d_m, events)."""
+    import pandas as pd
+    df = pd.read_csv(path, index_col=0, float_precision="round_trip")
+    table = df.to_numpy(dtype=np.float64)
+    return table[2:].copy(), table[0].copy(), table[1].copy(), list(df.columns)

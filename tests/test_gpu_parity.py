@@ -232,3 +232,130 @@ def test_alternative_kernel_paths_agree():
         s, g = res[name]
         assert abs(s - s0) <= 1e-12 * abs(s0), name
         assert rel_err(g, g0) <= 1e-11, name
+
+
+# ---- the configurations the bench numbers are quoted on ------------------------------------------------------------------
+
+def _restated_row(args):
+    from oracle import reference_restated as rr
+    th, dp, dm, row = args
+    r = rr.patient_value_grad(th, dp, dm, row, want_grad=True)
+    return None if r is None else (float(r[1]), np.concatenate([np.asarray(r[2], float).ravel(), np.asarray(r[3], float), np.asarray(r[4], float)]))
+
+
+@pytest.mark.parametrize("n,n_dat", [(25, 100000), (20, 10000)])
+def test_bench_dataset_rows_against_restated_reference(n, n_dat):
+    """Rows of the VERY datasets bench.py times (SYN-v1, BASELINE configs[3] and configs[2]): a stratified sample with every
+    (type, k) stratum up to 2^13 states (2^14 for pairs) against oracle/reference_restated.py -- per-row log-likelihood through
+    mmh_per_patient, gradient sums through mmh_eval_weighted."""
+    import multiprocessing as mp
+    import os
+    from metmhn_b200 import Handle
+    from metmhn_b200.simulate import syn_v1
+    d = syn_v1(n, n_dat, 1000 * n + 3)
+    dat, ep = d["dat"], d["eval_point"]
+    n_tot = n + 1
+    th, dp, dm = ep[:n_tot * n_tot].reshape(n_tot, n_tot), ep[n_tot * n_tot:n_tot * (n_tot + 1)], ep[n_tot * (n_tot + 1):]
+    typ = dat[:, -1]
+    pt = dat[:, 0:2 * n:2].astype(int).sum(axis=1)
+    mt = dat[:, 1:2 * n:2].astype(int).sum(axis=1)
+    k = np.where(typ == 3, pt + mt + 1, np.where(typ == 2, mt + 1, pt + dat[:, 2 * n]))
+    pick = []
+    for t in range(4):
+        for kk in range(0, 15 if t == 3 else 14):
+            idx = np.nonzero((typ == t) & (k == kk))[0]
+            pick.extend(idx[:2 if kk >= 12 else 3].tolist())
+    pick = np.asarray(sorted(pick))
+    assert len({(int(typ[i]), int(k[i])) for i in pick}) >= 45
+    sub = np.ascontiguousarray(dat[pick])
+    with mp.get_context("fork").Pool(min(os.cpu_count() or 1, 16)) as pool:
+        ref = pool.map(_restated_row, [(th, dp, dm, r) for r in sub], chunksize=1)
+    h = Handle(sub)
+    lp = h.per_patient(ep)
+    s, g = h.eval_weighted(ep, 1.0, 1.0)
+    S, G = 0.0, np.zeros(n_tot * (n_tot + 2))
+    for i, r in enumerate(ref):
+        assert r is not None
+        assert abs(lp[i] - r[0]) <= TOL * abs(r[0]), (i, int(typ[pick[i]]), int(k[pick[i]]))
+        S += r[0]
+        G += r[1]
+    assert abs(s - S) <= TOL * abs(S)
+    assert rel_err(g, G) <= TOL
+
+
+def test_tile_kernels_against_reference_golden_on_bench_rows():
+    """tests/golden/golden_big.npz: rows of the bench datasets with 2^13 ... 2^18-state lattices, evaluated by the UNMODIFIED
+    reference under the shim (tests/golden/make_golden_big.py).  Every row is solved by the big-tier kernels (tile solve,
+    fused group-B statistics, product-form marginals), so this compares them with reference-derived numbers directly."""
+    import os
+    from metmhn_b200 import Handle
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_big.npz")
+    gb = np.load(path)
+    for c in [str(x) for x in gb["cases"]]:
+        rows, ep = gb[f"{c}/rows"], gb[f"{c}/eval_point"]
+        n_tot = (rows.shape[1] - 3) // 2 + 1
+        bits = rows[:, :2 * (n_tot - 1) + 1].astype(int).sum(axis=1)
+        assert bits.max() >= 17
+        lp_all = Handle(rows).per_patient(ep)
+        for r in range(rows.shape[0]):
+            h = Handle(rows[r:r + 1])
+            s, g = h.eval_weighted(ep, 1.0, 1.0)
+            h.close()
+            ref = gb[f"{c}/row_logp"][r]
+            assert abs(s - ref) <= TOL * abs(ref), (c, r)
+            assert abs(lp_all[r] - ref) <= TOL * abs(ref), (c, r)
+            for got, key in zip(_split(g, n_tot), ("row_g", "row_gdp", "row_gdm")):
+                want = gb[f"{c}/{key}"][r]
+                if np.abs(want).max() == 0.0:
+                    assert np.abs(got).max() == 0.0, (c, r, key)
+                else:
+                    assert rel_err(got, want) <= TOL, (c, r, key)
+
+
+def test_per_patient_mirrors_of_the_reference_likelihood_module(golden):
+    """Every function of metmhn_b200/likelihood.py (the mirrors of metmhn/jx/likelihood.py:286-730 and one_event.py) against the
+    per-row goldens of the reference: each row of `kinds_n*` is sent through the function the reference's dispatch would call."""
+    from metmhn_b200 import likelihood as lk
+    called = set()
+    for c in [str(x) for x in golden["cases"]]:
+        if not c.startswith("kinds_n") or f"{c}/row_logp" not in golden.files:
+            continue
+        th, dp, dm, dat, _ = _case(golden, c)
+        n = th.shape[0] - 1
+        for r in range(dat.shape[0]):
+            row = dat[r]
+            typ, order = int(row[-1]), int(row[-2])
+            ref_lp = golden[f"{c}/row_logp"][r]
+            ref = (golden[f"{c}/row_g"][r], golden[f"{c}/row_gdp"][r], golden[f"{c}/row_gdm"][r])
+            state_pt = np.append(row[0:2 * n:2], row[2 * n])
+            state_mt = np.append(row[1:2 * n:2], row[2 * n])
+            n_prim, n_met = int(state_pt.sum()), int(state_mt.sum())
+            if typ in (0, 1):
+                if typ == 0 and n_prim == 0:
+                    lp, g, gdp = lk._grad_prim_obs_az(th)
+                    lp2 = lk._lp_prim_obs_az(th)
+                    called.update(["_grad_prim_obs_az", "_lp_prim_obs_az"])
+                else:
+                    lp, g, gdp = lk._grad_prim_obs(th, dp, state_pt, n_prim)
+                    lp2 = lk._lp_prim_obs(th, dp, state_pt, n_prim)
+                    called.update(["_grad_prim_obs", "_lp_prim_obs"])
+                gdm = np.zeros(n + 1)
+            elif typ == 2:
+                lp, g, gdp, gdm = lk._grad_met_obs(th, dp, dm, state_mt, n_met)
+                lp2 = lk._lp_met_obs(th, dp, dm, state_mt, n_met)
+                called.update(["_grad_met_obs", "_lp_met_obs"])
+            else:
+                o = order if order in (0, 1) else 2
+                fg = (lk._g_coupled_0, lk._g_coupled_1, lk._g_coupled_2)[o]
+                fl = (lk._lp_coupled_0, lk._lp_coupled_1, lk._lp_coupled_2)[o]
+                lp, g, gdp, gdm = fg(th, dp, dm, row[:2 * n + 1], n_prim, n_met)
+                lp2 = fl(th, dp, dm, row[:2 * n + 1], n_prim, n_met)
+                called.update([fg.__name__, fl.__name__])
+            assert abs(lp - ref_lp) <= TOL * abs(ref_lp) and abs(lp2 - ref_lp) <= TOL * abs(ref_lp), (c, r)
+            for got, want in zip((g, gdp, gdm), ref):
+                if np.abs(want).max() == 0.0:
+                    assert np.abs(got).max() == 0.0, (c, r)
+                else:
+                    assert rel_err(got, want) <= TOL, (c, r)
+    assert called == {"_g_coupled_0", "_g_coupled_1", "_g_coupled_2", "_lp_coupled_0", "_lp_coupled_1", "_lp_coupled_2",
+                      "_grad_prim_obs", "_lp_prim_obs", "_grad_prim_obs_az", "_lp_prim_obs_az", "_grad_met_obs", "_lp_met_obs"}

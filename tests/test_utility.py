@@ -36,3 +36,23 @@ def test_oracle_on_luad_subset_matches_reference():
         s, gg, a, b = mod.score_and_grad(g["theta"], g["d_p"], g["d_m"], g["rows"], 0.65)
         assert abs(s - g["score"]) <= 1e-10 * abs(g["score"])
         assert rel_err(gg, g["g"]) <= 1e-10 and rel_err(a, g["gdp"]) <= 1e-10 and rel_err(b, g["gdm"]) <= 1e-10
+
+
+def test_model_csv_round_trip_and_reference_layout(tmp_path):
+    """`row_stack(d_p, d_m, theta)` with the event names as columns (examples/analysis.py:115-120)."""
+    import os
+    from metmhn_b200.utility import read_model_csv, write_model_csv
+    rng = np.random.default_rng(3)
+    n_tot = 5
+    th, dp, dm = rng.normal(size=(n_tot, n_tot)), rng.normal(size=n_tot), rng.normal(size=n_tot)
+    names = ["TP53 (M)", "KRAS (M)", "EGFR (M)", "STK11 (M)", "Seeding"]
+    p = str(tmp_path / "model.csv")
+    write_model_csv(p, th, dp, dm, names)
+    lines = open(p).read().splitlines()
+    assert lines[0] == "," + ",".join(names) and len(lines) == 1 + 2 + n_tot and lines[1].startswith("0,") and lines[3].startswith("2,")
+    th2, dp2, dm2, names2 = read_model_csv(p)
+    assert names2 == names and np.array_equal(th2, th) and np.array_equal(dp2, dp) and np.array_equal(dm2, dm)
+    ref = "/root/reference/results/luad/luad_g14_20muts.csv"
+    if os.path.exists(ref):                       # the published model has the same layout (23 rows = d_p, d_m, 21 x 21 theta)
+        th3, dp3, dm3, names3 = read_model_csv(ref)
+        assert th3.shape == (21, 21) and dp3.shape == (21,) and names3[-1] == "Seeding"
