@@ -123,6 +123,21 @@ int mmh_multi_value_grad(mmh_multi* m, const double* params, double perc_met, do
 int mmh_multi_value(mmh_multi* m, const double* params, double perc_met, double* score);
 void mmh_multi_destroy(mmh_multi* m);
 
+/* learn_mhn (regularized_optimization.py:301-334) as ONE call: minimises -score + w_penal * symmetric_penal(params)
+ * (:46-52, smoothing eps, 1e-5 in the reference) from x0 with L-BFGS-B without bounds (m = 10, More'-Thuente line search,
+ * stopping tests of SciPy's driver: relative decrease <= ftol, max|gradient| <= 1e-5, max_iter iterations).  The
+ * likelihood, its gradient AND the penalty are evaluated on the device; the host keeps the limited-memory vectors.  x_out
+ * receives (n+1)(n+3) doubles; f_out, n_iter, n_eval may be NULL.  With a communicator attached (mmh_comm_init) every
+ * rank runs the same loop on the all-reduced objective. */
+int mmh_learn(mmh_handle* h, const double* x0, double perc_met, double w_penal, double eps, int64_t max_iter, double ftol,
+              double* x_out, double* f_out, int64_t* n_iter, int64_t* n_eval);
+
+/* GPU Gillespie sampler of the metMHN process (metmhn/simulations.py:8-147 `single_traject` / `simulate_dat`): n_sim
+ * trajectories, one thread each, Philox4x32-10 random numbers keyed by (seed, trajectory index).  geno receives n_sim rows
+ * of 2*n_mut+1 int8 [PT_0, MT_0, ..., PT_{n-1}, MT_{n-1}, seeding], order one int8 per row: 1 = PT diagnosed first,
+ * 2 = MT diagnosed first, 0 = the trajectory ended before seeding (never-metastasised primary tumour). */
+int mmh_simulate(int n_mut, const double* params, int64_t n_sim, uint64_t seed, int device, int8_t* geno, int8_t* order);
+
 int mmh_stats(mmh_handle* h, mmh_stats_t* out);
 void mmh_destroy(mmh_handle* h);
 const char* mmh_last_error(void);

@@ -22,7 +22,7 @@ EXPORTS = ("mmh_create", "mmh_value_grad", "mmh_value", "mmh_eval_weighted", "mm
            "mmh_set_profile", "mmh_per_patient",
            "mmh_stats", "mmh_destroy", "mmh_last_error", "mmh_measure_fp64_tflops",
            "mmh_nccl_unique_id", "mmh_comm_init", "mmh_comm_destroy",
-           "mmh_multi_create", "mmh_multi_value_grad", "mmh_multi_value", "mmh_multi_destroy")
+           "mmh_multi_create", "mmh_multi_value_grad", "mmh_multi_value", "mmh_multi_destroy", "mmh_simulate", "mmh_learn")
 
 
 class Stats(C.Structure):
@@ -72,6 +72,9 @@ def lib():
     L.mmh_multi_value.argtypes = [C.c_void_p, dp, C.c_double, dp]
     L.mmh_multi_destroy.argtypes = [C.c_void_p]
     L.mmh_multi_destroy.restype = None
+    L.mmh_simulate.argtypes = [C.c_int, dp, C.c_int64, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+    L.mmh_learn.argtypes = [C.c_void_p, dp, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_double, dp, dp,
+                            C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     for name in EXPORTS:
         if name not in ("mmh_destroy", "mmh_last_error", "mmh_multi_destroy"):
             getattr(L, name).restype = C.c_int
@@ -158,6 +161,16 @@ class Handle:
         d["k_hist"] = {t: {k: int(s.k_hist[t][k]) for k in range(64) if s.k_hist[t][k]} for t in range(4)}
         return d
 
+    def learn(self, x0, perc_met, w_penal, eps=1e-5, max_iter=100000, ftol=1e-4):
+        """The whole L-BFGS fit inside the library (mmh_learn): returns (x, f, iterations, evaluations)."""
+        p = self._params(x0)
+        x = np.empty(self.npar)
+        f = C.c_double()
+        it, ev = C.c_int64(), C.c_int64()
+        check(lib().mmh_learn(self._h, _dptr(p), float(perc_met), float(w_penal), float(eps), int(max_iter), float(ftol),
+                              _dptr(x), C.byref(f), C.byref(it), C.byref(ev)))
+        return x, f.value, it.value, ev.value
+
     def comm_init(self, unique_id: bytes, nranks: int, rank: int):
         """Attach an NCCL communicator (collective over all ranks): from now on every evaluation on this handle
         ends with an in-library all-reduce of the result on the handle's stream."""
@@ -228,6 +241,22 @@ class MultiHandle:
             self.close()
         except Exception:
             pass
+
+
+def simulate(log_theta, log_d_p, log_d_m, n_sim: int, seed: int = 0, device: int = 0):
+    """GPU Gillespie sampler (`metmhn/simulations.py:110-147` `simulate_dat`): returns (geno int8 (n_sim, 2n+1), order int8
+    (n_sim,)) with order 1 = PT diagnosed first, 2 = MT first, 0 = never seeded."""
+    th = np.asarray(log_theta, dtype=np.float64)
+    n_tot = th.shape[0]
+    p = np.ascontiguousarray(np.concatenate([th.ravel(), np.asarray(log_d_p, dtype=np.float64).ravel(),
+                                             np.asarray(log_d_m, dtype=np.float64).ravel()]))
+    if th.shape != (n_tot, n_tot) or p.shape[0] != n_tot * (n_tot + 2):
+        raise MetMHNError(MMH_EINVAL, "log_theta must be (n+1, n+1), log_d_p / log_d_m (n+1,)")
+    geno = np.zeros((int(n_sim), 2 * (n_tot - 1) + 1), dtype=np.int8)
+    order = np.zeros(int(n_sim), dtype=np.int8)
+    check(lib().mmh_simulate(n_tot - 1, _dptr(p), int(n_sim), int(seed) & 0xFFFFFFFFFFFFFFFF, int(device),
+                             geno.ctypes.data_as(C.c_void_p), order.ctypes.data_as(C.c_void_p)))
+    return geno, order
 
 
 def measure_fp64_tflops(device=0):

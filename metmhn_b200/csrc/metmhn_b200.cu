@@ -13,6 +13,8 @@
 
 #include "../../include/metmhn_b200.h"
 #include "mmh_device.cuh"
+#include "mmh_simulate.cuh"
+#include "mmh_lbfgs.hpp"
 
 using namespace mmh;
 
@@ -1135,6 +1137,111 @@ extern "C" int mmh_multi_value(mmh_multi* m, const double* params, double perc_m
 {
     if (!m || !params || !score) return fail(MMH_EINVAL, "mmh_multi_value: null argument");
     return multi_eval(m, params, perc_met, 0, score);
+}
+
+// ---- learn_mhn inside the library (regularized_optimization.py:270-334) ------------------------------------------------
+// out[0] = -score + lambda * penalty, out[1..] = -grad + lambda * penalty': `symmetric_penal` (:46-52) = the symmetrised group
+// penalty on the off-diagonal theta pairs (:31-43) + smoothed L1 on d_p, d_m (:11-28), on the device so that the objective of
+// an L-BFGS iteration is one stream of work and one 7 KB read-back.
+__global__ void k_penalty(const double* __restrict__ params, int n_tot, double eps, double lambda, double* __restrict__ out)
+{
+    __shared__ double red[1024];
+    const int sq = n_tot * n_tot;
+    double pen = 0.0;
+    for (int t = threadIdx.x; t < sq + 2 * n_tot; t += blockDim.x) {
+        double dpen;
+        if (t < sq) {
+            const int i = t / n_tot, j = t % n_tot;
+            if (i == j) { pen += sqrt(eps); dpen = 0.0; }                      // pair.sum() runs over the zeroed diagonal too
+            else {
+                const double a = params[t], b = params[j * n_tot + i];
+                const double pr = sqrt(a * a + b * b - a * b + eps);
+                pen += pr;
+                dpen = (2.0 * a - b) / (2.0 * pr);
+            }
+        } else {
+            const double d = params[t], r = sqrt(d * d + eps);
+            pen += 2.0 * r;                                                     // the theta part is halved below
+            dpen = d / r;
+        }
+        out[1 + t] = -out[1 + t] + lambda * dpen;
+    }
+    red[threadIdx.x] = pen;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = -out[0] + lambda * 0.5 * (red[0] - n_tot * sqrt(eps));
+}
+
+extern "C" int mmh_learn(mmh_handle* h, const double* x0, double perc_met, double w_penal, double eps, int64_t max_iter,
+                         double ftol, double* x_out, double* f_out, int64_t* n_iter, int64_t* n_eval)
+{
+    if (!h || !x0 || !x_out) return fail(MMH_EINVAL, "mmh_learn: null argument");
+    CK(cudaSetDevice(h->device));
+    double w0, w1;
+    class_weights(h, perc_met, w0, w1);
+    const size_t npar = (size_t)h->n_tot * (h->n_tot + 2);
+    std::vector<double> x(x0, x0 + npar);
+    int rc_eval = MMH_OK;
+    auto fun = [&](const double* xv, double* g) -> double {
+        cudaError_t e = cudaMemcpyAsync(h->d_params, xv, npar * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess) {
+            rc_eval = run_eval(h, h->d_params, w0, w1, 1);
+            if (rc_eval == MMH_OK) rc_eval = reduce_result(h, npar + 1);
+            if (rc_eval != MMH_OK) return std::nan("");
+            k_penalty<<<1, 1024, 0, h->stream>>>(h->d_params, h->n_tot, eps, w_penal, h->d_out);
+            e = cudaMemcpyAsync(h->h_out, h->d_out, (npar + 1) * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) { rc_eval = fail(MMH_ECUDA, std::string("mmh_learn: ") + cudaGetErrorString(e)); return std::nan(""); }
+        std::memcpy(g, h->h_out + 1, npar * sizeof(double));
+        return h->h_out[0];
+    };
+    const int iters = (int)std::min<int64_t>(std::max<int64_t>(max_iter, 0), 2000000000);
+    const LbfgsResult r = lbfgs_minimize(fun, x, iters, ftol);
+    if (r.status == -1) return rc_eval != MMH_OK ? rc_eval : fail(MMH_EINVAL, "mmh_learn: the objective is not finite at a trial point");
+    std::memcpy(x_out, x.data(), npar * sizeof(double));
+    if (f_out) *f_out = r.f;
+    if (n_iter) *n_iter = r.iterations;
+    if (n_eval) *n_eval = r.evaluations;
+    return MMH_OK;
+}
+
+// ---- GPU Gillespie sampler (metmhn/simulations.py:8-147) ----------------------------------------------------
+extern "C" int mmh_simulate(int n_mut, const double* params, int64_t n_sim, uint64_t seed, int device,
+                            int8_t* geno, int8_t* order)
+{
+    if (!params || !geno || !order || n_mut < 1 || n_mut > MMH_MAX_MUT || n_sim < 0)
+        return fail(MMH_EINVAL, "mmh_simulate: bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+        return fail(MMH_ECUDA, "mmh_simulate: no usable CUDA device (this library has no CPU fallback)");
+    if (n_sim == 0) return MMH_OK;
+    CK(cudaSetDevice(device));
+    const int n_tot = n_mut + 1;
+    const size_t npar = (size_t)n_tot * (n_tot + 2), width = (size_t)2 * n_mut + 1;
+    double* d_params = nullptr;
+    SimPar* d_par = nullptr;
+    int8_t *d_geno = nullptr, *d_order = nullptr;
+    auto cleanup = [&]() { cudaFree(d_params); cudaFree(d_par); cudaFree(d_geno); cudaFree(d_order); };
+    cudaError_t e = cudaMalloc((void**)&d_params, npar * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_par, sizeof(SimPar));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_geno, (size_t)n_sim * width);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_order, (size_t)n_sim);
+    if (e == cudaSuccess) e = cudaMemcpy(d_params, params, npar * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_sim_prep<<<1, 256>>>(d_params, n_tot, d_par);
+        k_simulate<<<(unsigned)((n_sim + 127) / 128), 128>>>(d_par, n_tot, n_sim, seed, d_geno, d_order);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(geno, d_geno, (size_t)n_sim * width, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(order, d_order, (size_t)n_sim, cudaMemcpyDeviceToHost);
+    cleanup();
+    if (e != cudaSuccess)
+        return fail(e == cudaErrorMemoryAllocation ? MMH_ENOMEM : MMH_ECUDA, std::string("mmh_simulate: ") + cudaGetErrorString(e));
+    return MMH_OK;
 }
 
 extern "C" const char* mmh_last_error(void) { return g_err.c_str(); }

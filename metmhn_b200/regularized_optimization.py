@@ -124,19 +124,44 @@ def score_and_grad_reg(params, dat, perc_met: float, penal: Callable, w_penal: f
     return np.array(-s + w_penal * pen), -g + w_penal * np.asarray(pen_)
 
 
-def learn_mhn(th_init, dp_init, dm_init, dat, perc_met: float, penal: Callable, w_penal: float,
-              opt_iter: int = 1e05, opt_ftol: float = 1e-04, opt_v: bool = True):
-    """Fit a metMHN with SciPy L-BFGS-B exactly as the reference drives it (reference :301-334)."""
-    import scipy.optimize as opt
+LAST_FIT: dict = {}
 
+
+def learn_mhn(th_init, dp_init, dm_init, dat, perc_met: float, penal: Callable, w_penal: float,
+              opt_iter: int = 1e05, opt_ftol: float = 1e-04, opt_v: bool = True, optimizer: str | None = None):
+    """Fit a metMHN (reference :301-334).
+
+    optimizer="scipy": SciPy's `minimize(method="L-BFGS-B")` calls `score_and_grad_reg` exactly as the reference drives it.
+    optimizer="native": the same algorithm (L-BFGS-B without bounds) inside the library, `mmh_learn`: likelihood, gradient
+    AND penalty on the device, one C call per fit -- no Python or SciPy work per iteration (SciPy >= 1.15 spends several
+    milliseconds per iteration in its own L-BFGS-B at these parameter counts, more than a LUAD evaluation takes on a B200).
+    Needs the built-in `symmetric_penal`.  Default (None): "native" when `penal` is `symmetric_penal`, else "scipy".
+    Both reach the same optimum; their iterates differ in the last digits, so the number of iterations can differ by a few.
+    `LAST_FIT` records {optimizer, f, iterations, evaluations} of the last call."""
     h = dataset_handle(dat)
     n_total = np.asarray(th_init).shape[0]
     x0 = _pack(th_init, dp_init, dm_init)
+    if optimizer is None:
+        optimizer = "native" if penal is symmetric_penal else "scipy"
+    if optimizer == "native":
+        if penal is not symmetric_penal:
+            raise ValueError("optimizer='native' evaluates symmetric_penal on the device; pass optimizer='scipy' for another penalty")
+        x, f, it, ev = h.learn(x0, perc_met, w_penal, eps=1e-05, max_iter=int(opt_iter), ftol=opt_ftol)
+        LAST_FIT.clear()
+        LAST_FIT.update(optimizer="native", f=f, iterations=it, evaluations=ev)
+        th, dp, dm = _unpack(x, n_total)
+        return th.copy(), dp.copy(), dm.copy()
+    if optimizer != "scipy":
+        raise ValueError("optimizer must be 'native', 'scipy' or None")
+    import scipy.optimize as opt
+
     options = {"maxiter": int(opt_iter), "ftol": opt_ftol}
     import scipy
     if tuple(int(v) for v in scipy.__version__.split(".")[:2]) < (1, 15):
         options["disp"] = opt_v           # SciPy >= 1.15 rewrote L-BFGS-B and no longer takes `disp`
     res = opt.minimize(fun=score_and_grad_reg, jac=True, x0=x0, method="L-BFGS-B",
                        args=(h, perc_met, penal, w_penal), options=options)
+    LAST_FIT.clear()
+    LAST_FIT.update(optimizer="scipy", f=float(res.fun), iterations=int(res.nit), evaluations=int(res.nfev))
     th, dp, dm = _unpack(res.x, n_total)
     return th.copy(), dp.copy(), dm.copy()

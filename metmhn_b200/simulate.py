@@ -84,6 +84,13 @@ def simulate(log_theta, log_d_p, log_d_m, n_sim: int, rng: np.random.Generator):
     return geno, order
 
 
+def simulate_gpu(log_theta, log_d_p, log_d_m, n_sim: int, seed: int = 0, device: int = 0):
+    """The same process on the GPU (mmh_simulate, one thread per trajectory): (geno, order) in the layout of `simulate`.
+    Different random stream than the NumPy sampler, same distribution (tests/test_gpu_workloads.py)."""
+    from ._lib import simulate as _sim
+    return _sim(log_theta, log_d_p, log_d_m, n_sim, seed, device)
+
+
 def syn_v1(n: int, n_dat: int, seed: int, max_joint_bits: int = 24, heavy: bool = False):
     """SYN-v1 dataset.  Returns dict(dat, theta, d_p, d_m, eval_point, perc_met).
 

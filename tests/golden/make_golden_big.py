@@ -48,34 +48,48 @@ def pick_rows(dat, n):
     return rows
 
 
-def main():
+def _one(args):
+    n, ep, row = args
     regopt, lik, one, van, kv = ref_under_shim.load()
     import jax.numpy as jnp
+    n_tot = n + 1
+    th, dp, dm = ep[:n_tot * n_tot].reshape(n_tot, n_tot), ep[n_tot * n_tot:n_tot * (n_tot + 1)], ep[n_tot * (n_tot + 1):]
+    t0 = time.time()
+    s, a, b, c = regopt.score_and_grad(jnp.array(th), jnp.array(dp), jnp.array(dm), jnp.array(row[None, :]), 0.65)
+    lp = float(np.asarray(s).reshape(-1)[0])
+    print(f"n={n} type {row[-1]} order {row[-2]} bits {int(row[:2 * n + 1].sum())}: logp {lp:.12f} ({time.time() - t0:.1f} s)", flush=True)
+    return lp, np.asarray(a), np.asarray(b), np.asarray(c)
+
+
+def main():
+    import multiprocessing as mp
     from metmhn_b200.simulate import syn_v1
 
-    out, cases = {}, []
+    out, cases, jobs, meta = {}, [], [], []
     for n, n_dat in ((25, 100000), (20, 10000)):
         d = syn_v1(n, n_dat, 1000 * n + 3)                      # the dataset bench.py times
         dat, ep = d["dat"], d["eval_point"]
-        n_tot = n + 1
-        th, dp, dm = ep[:n_tot * n_tot].reshape(n_tot, n_tot), ep[n_tot * n_tot:n_tot * (n_tot + 1)], ep[n_tot * (n_tot + 1):]
         rows = pick_rows(dat, n)
         if n == 20:
-            rows = rows[:6]
-        lp = np.zeros(len(rows))
-        g = np.zeros((len(rows), n_tot, n_tot))
-        gdp = np.zeros((len(rows), n_tot))
-        gdm = np.zeros((len(rows), n_tot))
-        for i, r in enumerate(rows):
-            t0 = time.time()
-            s, a, b, c = regopt.score_and_grad(jnp.array(th), jnp.array(dp), jnp.array(dm), jnp.array(dat[r:r + 1]), 0.65)
-            lp[i] = float(np.asarray(s).reshape(-1)[0])
-            g[i], gdp[i], gdm[i] = np.asarray(a), np.asarray(b), np.asarray(c)
-            print(f"n={n} row {r} type {dat[r, -1]} order {dat[r, -2]} bits {int(dat[r, :2 * n + 1].sum())}: logp {lp[i]:.12f} "
-                  f"({time.time() - t0:.1f} s)", flush=True)
+            rows = [r for r in rows if int(dat[r, :2 * n + 1].sum()) <= 16][:5]
+        meta.append((n, n_dat, dat, ep, rows))
+        jobs += [(n, ep, dat[r]) for r in rows]
+    # the big rows first: the pool finishes when the longest one does
+    order = sorted(range(len(jobs)), key=lambda i: -int(jobs[i][2][:-2].sum()) - (5 if jobs[i][2][-1] == 3 else 0))
+    with mp.get_context("spawn").Pool(min(len(jobs), max(1, (os.cpu_count() or 2) - 2))) as pool:
+        res_sorted = pool.map(_one, [jobs[i] for i in order], chunksize=1)
+    res = [None] * len(jobs)
+    for i, r in zip(order, res_sorted):
+        res[i] = r
+    pos = 0
+    for n, n_dat, dat, ep, rows in meta:
+        mine = res[pos:pos + len(rows)]
+        pos += len(rows)
         name = f"bench_n{n}"
-        for k, v in {"rows_index": np.asarray(rows), "rows": dat[rows], "eval_point": ep, "row_logp": lp, "row_g": g,
-                     "row_gdp": gdp, "row_gdm": gdm, "seed": np.int64(1000 * n + 3), "n_dat": np.int64(n_dat)}.items():
+        for k, v in {"rows_index": np.asarray(rows), "rows": dat[rows], "eval_point": ep,
+                     "row_logp": np.array([m[0] for m in mine]), "row_g": np.stack([m[1] for m in mine]),
+                     "row_gdp": np.stack([m[2] for m in mine]), "row_gdm": np.stack([m[3] for m in mine]),
+                     "seed": np.int64(1000 * n + 3), "n_dat": np.int64(n_dat)}.items():
             out[f"{name}/{k}"] = np.asarray(v)
         cases.append(name)
     out["cases"] = np.array(cases)

@@ -69,13 +69,22 @@ def test_learn_mhn_converges_and_matches_oracle_objective():
     lam = 1e-3
     x0 = np.concatenate([th0.ravel(), dp0, dm0])
     f0, _ = mm.score_and_grad_reg(x0, dat, 0.65, mm.symmetric_penal, lam)
-    th, dp, dm = mm.learn_mhn(th0, dp0, dm0, dat, 0.65, mm.symmetric_penal, lam, opt_ftol=1e-9, opt_v=False)
-    x = np.concatenate([th.ravel(), dp, dm])
-    f, g = mm.score_and_grad_reg(x, dat, 0.65, mm.symmetric_penal, lam)
-    assert float(f) < float(f0) - 1e-3
-    assert np.abs(g).max() < 5e-3
-    f_ref, g_ref = rr.score_and_grad_reg(x, dat, 0.65, rr.symmetric_penal, lam)
-    assert abs(float(f) - f_ref) <= 1e-10 * abs(f_ref) and rel_err(g, g_ref) <= 1e-8
+    fs = {}
+    for optimizer in ("native", "scipy"):          # the in-library loop (mmh_learn) and SciPy's driver reach the same optimum
+        th, dp, dm = mm.learn_mhn(th0, dp0, dm0, dat, 0.65, mm.symmetric_penal, lam, opt_ftol=1e-9, opt_v=False, optimizer=optimizer)
+        assert mm.regularized_optimization.LAST_FIT["optimizer"] == optimizer and mm.regularized_optimization.LAST_FIT["iterations"] > 5
+        x = np.concatenate([th.ravel(), dp, dm])
+        f, g = mm.score_and_grad_reg(x, dat, 0.65, mm.symmetric_penal, lam)
+        assert float(f) < float(f0) - 1e-3
+        assert np.abs(g).max() < 5e-3
+        f_ref, g_ref = rr.score_and_grad_reg(x, dat, 0.65, rr.symmetric_penal, lam)
+        assert abs(float(f) - f_ref) <= 1e-10 * abs(f_ref) and rel_err(g, g_ref) <= 1e-8
+        fs[optimizer] = float(f)
+    assert abs(fs["native"] - fs["scipy"]) <= 1e-7 * abs(fs["scipy"])
+    # the objective mmh_learn minimises is score_and_grad_reg: its reported minimum is the host-side value at the solution
+    assert abs(mm.regularized_optimization.LAST_FIT["f"] - fs["scipy"]) <= 1e-7 * abs(fs["scipy"])
+    with pytest.raises(ValueError):
+        mm.learn_mhn(th0, dp0, dm0, dat, 0.65, lambda p, n: mm.symmetric_penal(p, n), lam, optimizer="native")
 
 
 def test_cross_val_sweep_runs_on_gpu():
@@ -88,3 +97,52 @@ def test_cross_val_sweep_runs_on_gpu():
     assert runs.shape == (2, 2) and np.isfinite(runs).all() and (runs < 0).all()
     runs2 = cross_val_distributed(d["dat"], mm.symmetric_penal, np.array([1e-3, 1e-2]), 2, 0.65)
     assert np.abs(runs - runs2).max() <= 1e-9
+
+
+def test_gpu_gillespie_sampler_matches_process_and_likelihood():
+    """mmh_simulate (GPU, one thread per trajectory) against (1) the NumPy sampler that restates metmhn/simulations.py:8-77:
+    same marginals within binomial noise, and (2) the likelihood itself -- the reference's known-answer test
+    (/root/reference/tests/test_likelihood.py:31-132): the frequency of an observation among simulated trajectories equals
+    exp(score) of that observation (there to 2 significant digits with 1e5 draws; here within 4.5 sigma of 4e5 draws)."""
+    import metmhn_b200 as mm
+    from metmhn_b200.simulate import random_params, simulate, simulate_gpu
+    n, n_sim = 3, 400000
+    rng = np.random.default_rng(42)
+    th, dp, dm = random_params(n, rng, density=0.6, off_sd=0.6, d_sd=0.5)
+    th[np.arange(n + 1), np.arange(n + 1)] = [-0.3, -0.8, -1.1, -0.2]
+    g_gpu, o_gpu = simulate_gpu(th, dp, dm, n_sim, seed=7)
+    g_cpu, o_cpu = simulate(th, dp, dm, n_sim, np.random.default_rng(8))
+    assert g_gpu.shape == (n_sim, 2 * n + 1) and set(np.unique(g_gpu)) <= {0, 1} and set(np.unique(o_gpu)) <= {0, 1, 2}
+    # determinism and independence of the launch shape: same seed, same rows; another seed, other rows
+    g2, o2 = simulate_gpu(th, dp, dm, 1000, seed=7)
+    assert np.array_equal(g2, g_gpu[:1000]) and np.array_equal(o2, o_gpu[:1000])
+    assert not np.array_equal(simulate_gpu(th, dp, dm, 1000, seed=9)[0], g2)
+    # structural facts of the process: without seeding the MT copy equals the PT and the order is 0
+    ns = g_gpu[:, -1] == 0
+    assert np.array_equal(g_gpu[ns, 0:2 * n:2], g_gpu[ns, 1:2 * n:2]) and np.all(o_gpu[ns] == 0) and np.all(o_gpu[~ns] > 0)
+
+    def close(f1, f2, nn=n_sim):
+        p = 0.5 * (f1 + f2)
+        return abs(f1 - f2) <= 4.5 * np.sqrt(2.0 * p * (1.0 - p) / nn) + 1e-12
+    for c in range(2 * n + 1):
+        assert close(g_gpu[:, c].mean(), g_cpu[:, c].mean()), c
+    for o in (0, 1, 2):
+        assert close((o_gpu == o).mean(), (o_cpu == o).mean()), o
+
+    def freq_vs_score(mask, row):
+        f = mask.mean()
+        p = float(np.exp(mm.score(th, dp, dm, np.asarray(row, dtype=np.int8)[None, :], 0.0)))
+        assert abs(f - p) <= 4.5 * np.sqrt(p * (1.0 - p) / n_sim) + 1e-12, (row, f, p)
+    pt, mt, seed_col = g_gpu[:, 0:2 * n:2], g_gpu[:, 1:2 * n:2], g_gpu[:, -1]
+    # never-seeded primary tumours (type 0): empty, and with every mutation
+    freq_vs_score((seed_col == 0) & (pt.sum(1) == 0), [0] * (2 * n) + [0, -99, 0])
+    freq_vs_score((seed_col == 0) & (pt.sum(1) == n), [1] * (2 * n) + [0, -99, 0])
+    # PT of a metastasised patient, MT unobserved (type 1) / MT only (type 2): marginalise the other tumour
+    freq_vs_score((seed_col == 1) & (pt.sum(1) == n), [1, 0] * n + [1, -99, 1])
+    freq_vs_score((seed_col == 1) & (mt.sum(1) == n), [0, 1] * n + [1, -99, 2])
+    # paired observations with known and unknown order of diagnosis (type 3)
+    geno = [1, 1, 0, 1, 1, 0]
+    same = np.all(g_gpu[:, :2 * n] == np.asarray(geno, dtype=np.int8), axis=1) & (seed_col == 1)
+    freq_vs_score(same & (o_gpu == 1), geno + [1, 1, 3])
+    freq_vs_score(same & (o_gpu == 2), geno + [1, 2, 3])
+    freq_vs_score(same, geno + [1, 0, 3])
