@@ -8,7 +8,7 @@ L-BFGS-B calls `score_and_grad_reg` with the same `dat` at every iteration
 """
 from __future__ import annotations
 
-import zlib
+import hashlib
 from typing import Callable
 
 import numpy as np
@@ -20,22 +20,28 @@ _CACHE_MAX = 8
 
 
 def dataset_handle(dat, device: int = 0) -> Handle:
-    """Handle for `dat` on `device`, cached by content."""
+    """Handle for `dat` on `device`, cached by content (a 128-bit BLAKE2 digest of the int8 matrix: L-BFGS-B passes the same
+    `dat` at every iteration; callers that evaluate many times should pass the Handle itself and skip the hashing)."""
     if isinstance(dat, Handle):
         return dat
-    a = np.ascontiguousarray(np.asarray(dat), dtype=np.int8)
-    key = (a.shape, zlib.crc32(a.view(np.uint8).reshape(-1)), device)
+    raw = np.asarray(dat)
+    if raw.dtype != np.int8:
+        if raw.size and (raw.min() < -128 or raw.max() > 127):
+            raise ValueError("dat entries must fit int8 (genotypes 0/1, order, type)")
+        if raw.dtype.kind == "f" and raw.size and not np.all(raw == np.round(raw)):
+            raise ValueError("dat entries must be integers")
+    a = np.ascontiguousarray(raw, dtype=np.int8)
+    key = (a.shape, hashlib.blake2b(a.view(np.uint8).reshape(-1), digest_size=16).digest(), device)
     h = _CACHE.get(key)
     if h is None:
         if len(_CACHE) >= _CACHE_MAX:
-            _CACHE.pop(next(iter(_CACHE))).close()
+            _CACHE.pop(next(iter(_CACHE)))      # only the cache's reference goes; a handle somebody still holds stays valid
         h = _CACHE[key] = Handle(a, device=device)
     return h
 
 
 def clear_cache():
-    while _CACHE:
-        _CACHE.popitem()[1].close()
+    _CACHE.clear()
 
 
 def _pack(log_theta, log_d_p, log_d_m):
