@@ -96,6 +96,10 @@ int mmh_set_profile(mmh_handle* h, int on);
 /* Per-row log-likelihoods of the last evaluation's parameters (test hook).  Rows with an
  * unknown type get 0. */
 int mmh_per_patient(mmh_handle* h, const double* params, double* logp);
+/* The same with gradients (the per-patient `_g_coupled_{0,1,2}`, `_grad_prim_obs`, `_grad_met_obs` of
+ * metmhn/jx/likelihood.py:442-730): rows first_row .. first_row + n_rows - 1, each evaluated as its own one-row dataset
+ * with unit weights; logp[n_rows], grads[n_rows * (n+1)(n+3)] or NULL.  A test hook (milliseconds per row). */
+int mmh_per_patient_grads(mmh_handle* h, const double* params, int64_t first_row, int64_t n_rows, double* logp, double* grads);
 
 /* ---- multi-GPU: one handle per GPU, the shard results are summed by ONE in-library ncclAllReduce ----------
  * The reference sums per-patient results (regularized_optimization.py:187-267); with the dataset sharded over

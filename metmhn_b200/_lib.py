@@ -22,7 +22,7 @@ EXPORTS = ("mmh_create", "mmh_value_grad", "mmh_value", "mmh_eval_weighted", "mm
            "mmh_set_profile", "mmh_per_patient",
            "mmh_stats", "mmh_destroy", "mmh_last_error", "mmh_measure_fp64_tflops",
            "mmh_nccl_unique_id", "mmh_comm_init", "mmh_comm_destroy",
-           "mmh_multi_create", "mmh_multi_value_grad", "mmh_multi_value", "mmh_multi_destroy", "mmh_simulate", "mmh_learn")
+           "mmh_multi_create", "mmh_multi_value_grad", "mmh_multi_value", "mmh_multi_destroy", "mmh_simulate", "mmh_learn", "mmh_per_patient_grads")
 
 
 class Stats(C.Structure):
@@ -73,6 +73,7 @@ def lib():
     L.mmh_multi_destroy.argtypes = [C.c_void_p]
     L.mmh_multi_destroy.restype = None
     L.mmh_simulate.argtypes = [C.c_int, dp, C.c_int64, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+    L.mmh_per_patient_grads.argtypes = [C.c_void_p, dp, C.c_int64, C.c_int64, dp, dp]
     L.mmh_learn.argtypes = [C.c_void_p, dp, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_double, dp, dp,
                             C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     for name in EXPORTS:
@@ -152,6 +153,15 @@ class Handle:
         out = np.zeros(max(self.n_dat, 1))
         check(lib().mmh_per_patient(self._h, _dptr(p), _dptr(out)))
         return out[: self.n_dat]
+
+    def per_patient_grads(self, params, first_row=0, n_rows=None):
+        """(logp[n_rows], grads[n_rows, npar]) of single rows (test hook, mmh_per_patient_grads)."""
+        p = self._params(params)
+        n_rows = self.n_dat - first_row if n_rows is None else int(n_rows)
+        lp = np.zeros(max(n_rows, 1))
+        g = np.zeros((max(n_rows, 1), self.npar))
+        check(lib().mmh_per_patient_grads(self._h, _dptr(p), int(first_row), n_rows, _dptr(lp), _dptr(g)))
+        return lp[:n_rows], g[:n_rows]
 
     def stats(self):
         s = Stats()

@@ -89,6 +89,7 @@ struct mmh_handle {
     std::vector<cudaEvent_t> evpool;
     uint32_t max_joints = 0;
     mmh_stats_t st{};
+    std::vector<int8_t> rows;                    // copy of the data matrix (n_dat x (2n+3)), for the per-row test hook
     void* comm = nullptr;                        // ncclComm_t once mmh_comm_init ran: every evaluation ends with an all-reduce
     bool comm_owned = true;
 };
@@ -286,6 +287,8 @@ static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_da
     }
     h->st.n_em = h->n_em;
     h->st.alg_bytes = 32.0 * h->st.states_value_grad;
+    h->rows.resize((size_t)n_dat * (2 * n + 3));
+    for (int64_t p = 0; p < n_dat; ++p) std::memcpy(h->rows.data() + (size_t)p * (2 * n + 3), dat + p * row_stride, (size_t)(2 * n + 3));
 
     // ---- pack patients into scratch chunks (largest first) --------------------------------------------
     std::vector<int64_t> order((size_t)n_dat);
@@ -991,6 +994,29 @@ extern "C" int mmh_per_patient(mmh_handle* h, const double* params, double* logp
     int rc = mmh_eval_weighted(h, params, 1.0, 1.0, 0, &s, nullptr);
     if (rc != MMH_OK) return rc;
     if (h->n_dat) CK(cudaMemcpy(logp, h->d_logp, (size_t)h->n_dat * sizeof(double), cudaMemcpyDeviceToHost));
+    return MMH_OK;
+}
+
+// Per-row log-likelihood AND gradient (test hook, the per-patient `_g_coupled_*` / `_grad_*` of metmhn/jx/likelihood.py):
+// every requested row is evaluated as its own one-row dataset with unit weights.  Milliseconds per row -- not a data path.
+extern "C" int mmh_per_patient_grads(mmh_handle* h, const double* params, int64_t first_row, int64_t n_rows,
+                                     double* logp, double* grads)
+{
+    if (!h || !params || !logp || first_row < 0 || n_rows < 0 || first_row + n_rows > h->n_dat)
+        return fail(MMH_EINVAL, "mmh_per_patient_grads: bad arguments");
+    const int width = 2 * h->n + 3;
+    const size_t npar = (size_t)h->n_tot * (h->n_tot + 2);
+    std::vector<double> buf(npar + 1);
+    for (int64_t r = 0; r < n_rows; ++r) {
+        mmh_handle* one = nullptr;
+        int rc = mmh_create(&one, h->n, h->rows.data() + (size_t)(first_row + r) * width, 1, width, h->device, 0);
+        if (rc != MMH_OK) return rc;
+        rc = mmh_eval_weighted(one, params, 1.0, 1.0, grads ? 1 : 0, buf.data(), nullptr);
+        mmh_destroy(one);
+        if (rc != MMH_OK) return rc;
+        logp[r] = buf[0];
+        if (grads) std::memcpy(grads + (size_t)r * npar, buf.data() + 1, npar * sizeof(double));
+    }
     return MMH_OK;
 }
 

@@ -49,7 +49,9 @@ def test_every_patient_kind_against_reference_golden(golden):
         th, dp, dm, dat, _ = _case(golden, c)
         params = np.concatenate([th.ravel(), dp, dm])
         n_tot = th.shape[0]
-        lp_all = Handle(dat).per_patient(params)
+        hall = Handle(dat)
+        lp_all = hall.per_patient(params)
+        lp_g, g_all = hall.per_patient_grads(params)                 # mmh_per_patient_grads: same numbers as one handle per row
         for r in range(dat.shape[0]):
             h = Handle(dat[r:r + 1])
             s, g = h.eval_weighted(params, 1.0, 1.0)
@@ -57,6 +59,7 @@ def test_every_patient_kind_against_reference_golden(golden):
             ref = golden[f"{c}/row_logp"][r]
             assert abs(s - ref) <= TOL * abs(ref), (c, r)
             assert abs(lp_all[r] - ref) <= TOL * abs(ref), (c, r)
+            assert lp_g[r] == s and np.array_equal(g_all[r], g), (c, r)
             for got, key in zip(_split(g, n_tot), ("row_g", "row_gdp", "row_gdm")):
                 want = golden[f"{c}/{key}"][r]
                 if np.abs(want).max() == 0.0:
