@@ -1631,13 +1631,6 @@ k_pf_hi(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, dou
 //            bits is known at compile time, the higher bits are uniform over the tile.
 // The per-item results go into one shared accumulator per CTA in a fixed warp order (no atomics): repeated
 // evaluations are bit-identical.
-#define MMH_STR_(x) #x
-#define MMH_PRAGMA_UNROLL_(n) _Pragma(MMH_STR_(unroll n))
-#ifdef FIN_UNROLL
-#define MMH_FIN_UNROLL MMH_PRAGMA_UNROLL_(FIN_UNROLL)
-#else
-#define MMH_FIN_UNROLL
-#endif
 constexpr int NACC = 3;                               // effective-parameter spaces: theta, theta_pt/d_p, theta/d_m
 constexpr int FIN_WARPS = 4;
 template <int MB>
@@ -1709,7 +1702,6 @@ k_finish(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, ui
                 // ---- phase 1: lane = sub-state ----
                 double gg = 0.0, xv = 0.0, yv = 0.0;
                 if (uv && !pmode) { if (joint) gg = st[u]; else { xv = x[u]; yv = y[u]; gg = xv * yv; } }
-                MMH_FIN_UNROLL
                 for (int r = 0; r < NR; ++r) {
                     const int rb = __shfl_sync(0xffffffffu, abit, r);
                     const bool rrow = r < nrows, rps = (r == ROW_DP || r == ROW_DM) && has_pseudo;
