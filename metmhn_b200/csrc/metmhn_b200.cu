@@ -13,6 +13,7 @@
 
 #include "../../include/metmhn_b200.h"
 #include "mmh_device.cuh"
+#include "mmh_rowblock.cuh"
 #include "mmh_simulate.cuh"
 #include "mmh_lbfgs.hpp"
 
@@ -40,11 +41,13 @@ struct ChunkPlan {
     uint64_t space0 = 0;
     uint32_t nspaces = 0;
     Range pre4, main_small4, sec_small4;         // small-tier spaces with K >= 7 (four states per lane)
+    Range rb_list;                               // pairs of the row-block kernel
     Range setup, setup_wide, diag, pre, main_small, sec_small, logp, joints, st_a, st_ar, st_b, pf_lo, pf_hi, fin;
     bool wide = false;                           // some group has more than MAXT bits
     std::vector<Range> main_lv, sec_lv;          // big-tier segments per popcount level (generic kernel)
     std::vector<Range> main_lvt, sec_lvt;        // big-tier tiles per level (tiled kernel)
     std::vector<Range> main_lvt_adj, main_lvt_adjb;  // adjoint pass of the main tiled spaces: plain / with fused B statistics
+    std::vector<Range> main_rb;                  // row-block kernel: blocks per OUTER level (both passes)
     uint64_t scratch = 0;                        // doubles
 };
 
@@ -64,6 +67,7 @@ struct mmh_handle {
     Item* d_items = nullptr;
     uint32_t* d_hs = nullptr;
     uint32_t* d_hsidx = nullptr;                 // [bits][level] -> first entry of that popcount level in d_hs
+    uint16_t* d_rblv = nullptr;                  // row-block kernel: level lists in a bank-conflict-free order
     int nsm = 0;
     uint8_t* d_cls = nullptr;
     double* d_cnt = nullptr;
@@ -94,7 +98,19 @@ struct mmh_handle {
     bool comm_owned = true;
 };
 
-// pairs whose adjoint solve also produces the group-B statistics (k_solve_tile_adjb); needs splitA/splitB
+// MMH_ROWBLK=1 sends the pairs to the shared-memory row-block kernel instead of the tile kernels (measured slower, kept
+// for experiments and covered by the parity tests); read once per process, so the plan and the launches always agree
+static bool use_rb()
+{
+    static const bool on = [] { const char* e = std::getenv("MMH_ROWBLK"); return e && std::atoi(e) != 0; }();
+    return on;
+}
+// pairs solved by the row-block kernel (k_solve_rb, mmh_rowblock.cuh): plain tables, at least 7 PT bits
+static bool rb_space(const SpaceDev& s)
+{
+    return use_rb() && s.kind == K_JOINT && !s.splitA && !s.splitB && s.KA >= RB_MINKA && (int)s.KA + (int)s.KB >= BIGK;
+}
+// pairs whose adjoint solve also produces the group-B statistics (k_solve_rb / k_solve_tile_adjb); needs splitA/splitB
 static bool fused_b(const SpaceDev& s)
 {
     return s.kind == K_JOINT && !s.splitA && !s.splitB && s.KA >= 4 && (int)s.KA + (int)s.KB >= BIGK;
@@ -131,7 +147,7 @@ static uint64_t space_scratch(SpaceDev& s, uint64_t off)
     s.tabB = s.kind == K_JOINT ? table(s.KB, s.splitB) : 0;
     s.y_off = take(N);
     s.x_off = take(N);
-    s.stA = s.stB = s.stP = s.stPB = 0;
+    s.stA = s.stB = s.stP = s.stPB = s.tabR = 0;
     s.slices = 1; s.slicesB = 1;
     if (s.kind == K_JOINT) {
         // group-A statistics sum over uB, group-B statistics over uA: slice the summed range so that lopsided pairs
@@ -142,10 +158,12 @@ static uint64_t space_scratch(SpaceDev& s, uint64_t off)
         s.slices = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(256, capA), std::max<uint64_t>(1, NB / 128));
         s.slicesB = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(256, capB), std::max<uint64_t>(1, NA / 2048));
         if (fused_b(s)) s.slicesB = adjb_slots(s.KA - 4, nullptr);     // one partial table per (lA, column chunk)
+        if (rb_space(s)) s.slicesB = 1u << std::max(0, (int)s.KA - RB_KI);   // one per value of the outer column bits
         s.stA = take((s.KA + 1) * NA);
         s.stB = take((s.KB + 1) * NB);
         s.stP = take((uint64_t)s.slices * (s.KA + 1) * NA);
         s.stPB = take((uint64_t)s.slicesB * (s.KB + 1) * NB);
+        if (rb_space(s)) s.tabR = take(RB_TABR);
     } else if (s.kind != K_PRE && s.splitA) {
         // product-form gradient: weighted marginals over the low / high part (k_pfin_lo / k_pfin_hi)
         const uint64_t N1 = 1ull << s.splitA, N2 = 1ull << (s.KA - s.splitA);
@@ -337,7 +355,7 @@ static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_da
             const uint32_t base_idx = (uint32_t)(spaces.size() - ck.space0);
             for (SpaceDev s : pp.sp) {
                 s.y_off += used; s.x_off += used; s.tabA += used;
-                if (s.kind == K_JOINT) { s.tabB += used; s.stA += used; s.stB += used; s.stP += used; s.stPB += used; }
+                if (s.kind == K_JOINT) { s.tabB += used; s.stA += used; s.stB += used; s.stP += used; s.stPB += used; if (s.tabR) s.tabR += used; }
                 else if (s.stP) s.stP += used;                  // product-form single-tumour spaces
                 if (s.joint >= 0) s.joint += base_idx;
                 if (s.pre >= 0) s.pre += base_idx;
@@ -371,6 +389,7 @@ static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_da
         ck.sec_small4 = list_of([&](const SpaceDev& s) { return is_sec(s) && bits(s) >= 7 && bits(s) < BIGK; });
         ck.logp = list_of([&](const SpaceDev& s) { return is_main(s); });
         ck.joints = list_of([&](const SpaceDev& s) { return s.kind == K_JOINT; });
+        ck.rb_list = list_of([&](const SpaceDev& s) { return rb_space(s); });
         h->max_joints = std::max(h->max_joints, ck.joints.cnt);
         ck.setup.off = items.size();
         auto setup_items = [&](uint32_t i, uint32_t g, int KG, int K1) {
@@ -402,19 +421,19 @@ static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_da
         ck.diag.cnt = (uint32_t)(items.size() - ck.diag.off);
         // spaces the tiled solve kernel takes (must agree with tiled_space() on the device side)
         auto tiled = [&](const SpaceDev& s) {
-            if (bits(s) < BIGK || s.kind == K_PRE) return false;
+            if (bits(s) < BIGK || s.kind == K_PRE || rb_space(s)) return false;
             if (s.kind == K_JOINT) return !s.splitA && !s.splitB && s.KA >= 4;
             return s.splitA >= 4;
         };
         auto levels_of = [&](auto pred, std::vector<Range>& lv) {
             int maxkh = -1;
-            for (uint32_t i = 0; i < ck.nspaces; ++i) if (pred(sp[i]) && bits(sp[i]) >= BIGK && !tiled(sp[i])) maxkh = std::max(maxkh, bits(sp[i]) - 7);
+            for (uint32_t i = 0; i < ck.nspaces; ++i) if (pred(sp[i]) && bits(sp[i]) >= BIGK && !tiled(sp[i]) && !rb_space(sp[i])) maxkh = std::max(maxkh, bits(sp[i]) - 7);
             if (maxkh < 0) return;
             lv.resize(maxkh + 1);
             for (int l = 0; l <= maxkh; ++l) {
                 lv[l].off = items.size();
                 for (uint32_t i = 0; i < ck.nspaces; ++i) {
-                    if (!pred(sp[i]) || bits(sp[i]) < BIGK || tiled(sp[i])) continue;
+                    if (!pred(sp[i]) || bits(sp[i]) < BIGK || tiled(sp[i]) || rb_space(sp[i])) continue;
                     const int kh = bits(sp[i]) - 7;          // blocks of 128 states
                     if (l > kh) continue;
                     need_hs(kh);
@@ -468,13 +487,13 @@ static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_da
         auto levels_of_adjb = [&](std::vector<Range>& lv) {
             int maxl = -1;
             for (uint32_t i = 0; i < ck.nspaces; ++i)
-                if (fused_b(sp[i])) maxl = std::max(maxl, (int)sp[i].KA - 4 + (int)sp[i].KB);
+                if (fused_b(sp[i]) && !rb_space(sp[i])) maxl = std::max(maxl, (int)sp[i].KA - 4 + (int)sp[i].KB);
             if (maxl < 0) return;
             lv.resize(maxl + 1);
             for (int l = 0; l <= maxl; ++l) {
                 lv[l].off = items.size();
                 for (uint32_t i = 0; i < ck.nspaces; ++i) {
-                    if (!fused_b(sp[i])) continue;
+                    if (!fused_b(sp[i]) || rb_space(sp[i])) continue;
                     const int kbA = sp[i].KA - 4, kbB = sp[i].KB;
                     if (l > kbA + kbB) continue;
                     need_hs(kbA); need_hs(kbB);
@@ -496,6 +515,33 @@ static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_da
                 lv[l].cnt = (uint32_t)(items.size() - lv[l].off);
             }
         };
+        // row-block kernel: a CTA is a block of 2^12 states = R rows x 2^KI columns; launch levels over the outer bits
+        {
+            int maxl = -1;
+            auto outer = [&](const SpaceDev& s) { return (int)s.KB + std::max(0, (int)s.KA - RB_KI); };
+            for (uint32_t i = 0; i < ck.nspaces; ++i) if (rb_space(sp[i])) maxl = std::max(maxl, outer(sp[i]));
+            ck.main_rb.resize(maxl + 1);
+            for (int l = 0; l <= maxl; ++l) {
+                ck.main_rb[l].off = items.size();
+                // fat levels: up to RB_MAXBLK blocks per CTA (the per-CTA tables are loaded once)
+                uint64_t total = 0;
+                for (int pass = 0; pass < 2; ++pass) {
+                    const uint32_t per_cta = (uint32_t)std::min<uint64_t>(RB_MAXBLK, std::max<uint64_t>(1, total / (148ull * 8)));
+                    for (uint32_t i = 0; i < ck.nspaces; ++i) {
+                        if (!rb_space(sp[i])) continue;
+                        const int KO = outer(sp[i]);
+                        if (l > KO) continue;
+                        const int KI = std::min<int>(sp[i].KA, RB_KI);
+                        need_hs(KO); need_hs(KI - 2);
+                        const uint32_t nL = hs_lvl[KO][l + 1] - hs_lvl[KO][l], R = 1u << (RB_KI - KI);
+                        if (pass == 0) { total += (nL + R - 1) / R; continue; }
+                        for (uint32_t f = 0; f < nL; f += R * per_cta)
+                            items.push_back({i, (uint32_t)l | (std::min(R * per_cta, nL - f) << 8), f});
+                    }
+                }
+                ck.main_rb[l].cnt = (uint32_t)(items.size() - ck.main_rb[l].off);
+            }
+        }
         levels_of(is_main, ck.main_lv);
         levels_of(is_sec, ck.sec_lv);
         levels_of_t(is_main, ck.main_lvt);
@@ -577,6 +623,26 @@ static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_da
             for (size_t l = 0; l < hs_lvl[kb].size() && l < 32; ++l) hsidx[(size_t)kb * 32 + l] = (uint32_t)(hs_off[kb] + hs_lvl[kb][l]);
         CK(up((void**)&h->d_hsidx, hsidx.data(), hsidx.size() * sizeof(uint32_t)));
     }
+    {
+        // Level lists of the row-block kernel, [bits][2^10]: popcount-sorted like d_hs, but inside a level the entries
+        // are dealt round-robin from the eight residue classes modulo 8, so that eight consecutive lanes touch eight
+        // different 16-byte bank groups of the shared-memory block (mmh_rowblock.cuh)
+        std::vector<uint16_t> rblv((size_t)(RB_KI - 1) << (RB_KI - 2), 0);
+        for (int kg = 0; kg <= RB_KI - 2; ++kg) {
+            size_t pos = (size_t)kg << (RB_KI - 2);
+            for (int l = 0; l <= kg; ++l) {
+                std::vector<uint16_t> bucket[8];
+                for (uint32_t c = 0; c < (1u << kg); ++c) if (__builtin_popcount(c) == l) bucket[c & 7u].push_back((uint16_t)c);
+                size_t taken[8] = {};
+                for (bool any = true; any;) {
+                    any = false;
+                    for (int k = 0; k < 8; ++k)
+                        if (taken[k] < bucket[k].size()) { rblv[pos++] = bucket[k][taken[k]++]; any = true; }
+                }
+            }
+        }
+        CK(up((void**)&h->d_rblv, rblv.data(), rblv.size() * sizeof(uint16_t)));
+    }
     CK(up((void**)&h->d_cls, cls.data(), cls.size()));
     CK(up((void**)&h->d_cnt, cnt_dm2.data(), NR * sizeof(double)));
     const size_t npar = (size_t)h->n_tot * (h->n_tot + 2);
@@ -605,6 +671,8 @@ static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_da
     CK(cudaEventCreate(&h->ev1));
     CK(cudaFuncSetAttribute(k_finish<MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIN_SMEM));
     CK(cudaFuncSetAttribute(k_finish<MAXG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIN_SMEM));
+    CK(cudaFuncSetAttribute(k_solve_rb<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RbSmem)));
+    CK(cudaFuncSetAttribute(k_solve_rb<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RbSmem)));
     h->st.scratch_bytes = (double)max_scratch * 8.0 * h->ns;
     return MMH_OK;
 }
@@ -682,14 +750,25 @@ static int enqueue_eval(mmh_handle* h, const double* d_params, double w0, double
                 ++launches;
             }
         };
+        auto rowblk = [&](bool adj) {
+            const int L = (int)ck.main_rb.size();
+            for (int q = 0; q < L; ++q) {
+                const Range& r = ck.main_rb[adj ? L - 1 - q : q];
+                if (!r.cnt) continue;
+                if (adj) k_solve_rb<true><<<r.cnt, RB_T, sizeof(RbSmem), st>>>(sp, h->d_items + r.off, h->d_hs, h->d_hsidx, h->d_rblv, S);
+                else     k_solve_rb<false><<<r.cnt, RB_T, sizeof(RbSmem), st>>>(sp, h->d_items + r.off, h->d_hs, h->d_hsidx, h->d_rblv, S);
+                ++launches;
+            }
+        };
         tick(0);
         k_setup<<<ck.setup.cnt, 256, 0, st>>>(sp, h->d_items + ck.setup.off, h->d_par, S); ++launches;
         if (ck.setup_wide.cnt) { k_setup_wide<<<ck.setup_wide.cnt, 1024, 0, st>>>(sp, h->d_items + ck.setup_wide.off, h->d_par, S); ++launches; }
         if (ck.diag.cnt) { k_diag_prod<<<ck.diag.cnt, 256, 0, st>>>(sp, h->d_items + ck.diag.off, S); ++launches; }
+        if (ck.rb_list.cnt) { k_rb_tables<<<ck.rb_list.cnt, 256, 0, st>>>(sp, h->d_lists + ck.rb_list.off, h->d_par, S); ++launches; }
         tick(1);
         small(ck.pre, false); small4(ck.pre4, false);
         small(ck.main_small, false); small4(ck.main_small4, false);
-        big(ck.main_lv, false); bigt(ck.main_lvt, false);
+        big(ck.main_lv, false); bigt(ck.main_lvt, false); rowblk(false);
         small(ck.sec_small, false); small4(ck.sec_small4, false);
         big(ck.sec_lv, false); bigt(ck.sec_lvt, false);
         tick(5);
@@ -713,6 +792,7 @@ static int enqueue_eval(mmh_handle* h, const double* d_params, double w0, double
             k_solve_tile_adjb<<<r.cnt, 256, 0, st>>>(sp, h->d_items + r.off, h->d_hs, h->d_hsidx, S);
             ++launches;
         }
+        rowblk(true);
         small(ck.pre, true); small4(ck.pre4, true);
         tick(3);
         if (ck.st_a.cnt) {
@@ -802,6 +882,15 @@ static int run_eval(mmh_handle* h, const double* d_params, double w0, double w1,
     h->st.n_launches = hit->launches;
     return MMH_OK;
 }
+
+#ifdef RB_TIMING
+extern "C" int mmh_debug_rb_timing(unsigned long long* out16, int reset)
+{
+    if (cudaMemcpyFromSymbol(out16, rb_timing, 16 * sizeof(unsigned long long)) != cudaSuccess) return MMH_ECUDA;
+    if (reset) { unsigned long long z[16] = {}; cudaMemcpyToSymbol(rb_timing, z, sizeof(z)); }
+    return MMH_OK;
+}
+#endif
 
 static void class_weights(const mmh_handle* h, double perc_met, double& w0, double& w1)
 {
@@ -1032,7 +1121,7 @@ extern "C" void mmh_destroy(mmh_handle* h)
     if (!h) return;
     cudaSetDevice(h->device);
     mmh_comm_destroy(h);
-    cudaFree(h->d_spaces); cudaFree(h->d_lists); cudaFree(h->d_items); cudaFree(h->d_hs); cudaFree(h->d_hsidx); cudaFree(h->d_cls);
+    cudaFree(h->d_spaces); cudaFree(h->d_lists); cudaFree(h->d_items); cudaFree(h->d_hs); cudaFree(h->d_hsidx); cudaFree(h->d_rblv); cudaFree(h->d_cls);
     cudaFree(h->d_cnt); cudaFree(h->d_par); cudaFree(h->d_params); cudaFree(h->d_logp);
     for (int q = 0; q < mmh_handle::NS; ++q) {
         cudaFree(h->d_scratch_s[q]);

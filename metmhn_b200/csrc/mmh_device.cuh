@@ -41,6 +41,7 @@ struct SpaceDev {
     uint64_t y_off, x_off;           // scratch offsets (in doubles)
     uint64_t tabA, tabB;             // NR x NA and NR x NB rate / diagonal tables
     uint64_t stA, stB, stP;          // joint only: marginal statistics ((KA+1) x NA, (KB+1) x NB, partials)
+    uint64_t tabR;                   // pairs of the row-block kernel: extra rate factors (mmh_rowblock.cuh)
     uint8_t  evA[MAXG], evB[MAXG];   // event id of every bit
 };
 

@@ -209,8 +209,8 @@ def test_tile_kernel_shapes_against_oracle():
 
 
 def test_alternative_kernel_paths_agree():
-    """The experimental row-block solve (MMH_ROWBLOCK=1), the SM-local work queues (MMH_SMLOCAL=1, every tile launch)
-    and the unfused statistics path (MMH_FUSE_B=0) give the default path's numbers (the switches are read once per
+    """MMH_ROWBLK=1 sends the pairs to the shared-memory row-block kernel (k_solve_rb, mmh_rowblock.cuh) instead of the
+    tile kernels (k_solve_tile / k_solve_tile_adjb).  Both paths give the same numbers (the switch is read once per
     process: run each in a fresh interpreter)."""
     import os
     import subprocess
@@ -224,17 +224,15 @@ def test_alternative_kernel_paths_agree():
             "s, g = Handle(d['dat']).value_grad(d['eval_point'], 0.65)\n"
             "print(repr(float(s))); print(' '.join(repr(float(v)) for v in g))\n") % root
     res = {}
-    for name, env in (("default", {}), ("rowblock", {"MMH_ROWBLOCK": "1"}), ("unfused", {"MMH_FUSE_B": "0"}),
-                      ("smlocal", {"MMH_SMLOCAL": "1", "MMH_SMLOCAL_MIN": "0"})):
+    for name, env in (("default", {}), ("rowblock", {"MMH_ROWBLK": "1"})):
         out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True)
         assert out.returncode == 0, out.stderr[-2000:]
         lines = out.stdout.strip().splitlines()
         res[name] = (float(lines[-2]), np.array([float(v) for v in lines[-1].split()]))
     s0, g0 = res["default"]
-    for name in ("rowblock", "unfused", "smlocal"):
-        s, g = res[name]
-        assert abs(s - s0) <= 1e-12 * abs(s0), name
-        assert rel_err(g, g0) <= 1e-11, name
+    s, g = res["rowblock"]
+    assert abs(s - s0) <= 1e-12 * abs(s0)
+    assert rel_err(g, g0) <= 1e-11
 
 
 # ---- the configurations the bench numbers are quoted on ------------------------------------------------------------------
