@@ -235,6 +235,32 @@ def test_alternative_kernel_paths_agree():
     assert rel_err(g, g0) <= 1e-11
 
 
+def test_wide_pairs_against_oracle():
+    """Pairs with a group of more than 16 bits (product tables, generic solve kernel): wide PT side with shared events,
+    wide MT side, against the lattice oracle."""
+    from metmhn_b200 import Handle
+    from oracle import lattice_direct as ld
+    n = 21
+    rng = np.random.default_rng(2121)
+    th = rng.normal(0.0, 0.3, (n + 1, n + 1))
+    th[np.arange(n + 1), np.arange(n + 1)] = rng.normal(-1.0, 0.5, n + 1)
+    dp, dm = rng.normal(0, 0.3, n + 1), rng.normal(0, 0.3, n + 1)
+    ev = list(range(n))
+    rows = np.stack([
+        _pair_row(n, ev[:17], ev[15:18], 1),          # KA = 17, KB = 3, two shared events, PT first
+        _pair_row(n, ev[:18], [0, 19], 0),            # KA = 18, KB = 2, unknown order
+        _pair_row(n, ev[13:18], ev[:17], 2),          # KA = 5, KB = 17 (wide MT side), MT first
+    ])
+    params = np.concatenate([th.ravel(), dp, dm])
+    for r in range(rows.shape[0]):
+        h = Handle(rows[r:r + 1])
+        s, g = h.eval_weighted(params, 1.0, 1.0)
+        h.close()
+        out = ld.patient_value_grad(th, dp, dm, rows[r])
+        assert abs(s - out[1]) <= TOL * abs(out[1]), r
+        assert rel_err(g, np.concatenate([out[2].ravel(), out[3], out[4]])) <= TOL, r
+
+
 # ---- the configurations the bench numbers are quoted on ------------------------------------------------------------------
 
 def _restated_row(args):
