@@ -42,7 +42,7 @@ struct ChunkPlan {
     uint32_t nspaces = 0;
     Range pre4, main_small4, sec_small4;         // small-tier spaces with K >= 7 (four states per lane)
     Range rb_list;                               // pairs of the row-block kernel
-    Range setup, setup_wide, diag, pre, main_small, sec_small, logp, joints, st_a, st_ar, st_b, pf_lo, pf_hi, fin;
+    Range setup, setup_wide, diag, pre, main_small, sec_small, logp, joints, st_a, st_ar, st_b, pf_lo, fin;
     bool wide = false;                           // some group has more than MAXT bits
     std::vector<Range> main_lv, sec_lv;          // big-tier segments per popcount level (generic kernel)
     std::vector<Range> main_lvt, sec_lvt;        // big-tier tiles per level (tiled kernel)
@@ -168,7 +168,7 @@ static uint64_t space_scratch(SpaceDev& s, uint64_t off)
         // product-form gradient: weighted marginals over the low / high part (k_pfin_lo / k_pfin_hi)
         const uint64_t N1 = 1ull << s.splitA, N2 = 1ull << (s.KA - s.splitA);
         s.slices = (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(1, N2 / 8));
-        s.stP = take((uint64_t)s.slices * (NR + s.KA) * N1 + (uint64_t)(NR + s.KA) * N2);
+        s.stP = take((uint64_t)s.slices * (NR + s.KA) * N1 + std::max<uint64_t>(1, N1 >> 7) * (NR + s.KA) * N2);   // k_pf partials
     }
     return off;
 }
@@ -579,13 +579,6 @@ static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_da
                     for (uint32_t c = 0; c < nch; ++c) items.push_back({i, c, sl});
             }
         ck.pf_lo.cnt = (uint32_t)(items.size() - ck.pf_lo.off);
-        ck.pf_hi.off = items.size();
-        for (uint32_t i = 0; i < ck.nspaces; ++i)
-            if (is_prod(sp[i])) {
-                const uint32_t N2 = 1u << (sp[i].KA - sp[i].splitA);
-                for (uint32_t u = 0; u < N2; u += PF_HB) items.push_back({i, u / PF_HB, 0u});
-            }
-        ck.pf_hi.cnt = (uint32_t)(items.size() - ck.pf_hi.off);
         ck.fin.off = items.size();
         for (uint32_t i = 0; i < ck.nspaces; ++i) {
             if (is_prod(sp[i])) {
@@ -803,9 +796,8 @@ static int enqueue_eval(mmh_handle* h, const double* d_params, double w0, double
         }
         tick(6);
         if (ck.pf_lo.cnt) {
-            k_pf_lo<<<ck.pf_lo.cnt, 32 * PF_WARPS, 0, st>>>(sp, h->d_items + ck.pf_lo.off, S);
-            k_pf_hi<<<ck.pf_hi.cnt, 32 * PF_WARPS, 0, st>>>(sp, h->d_items + ck.pf_hi.off, S);
-            launches += 2;
+            k_pf<<<ck.pf_lo.cnt, 32 * PF_WARPS, 0, st>>>(sp, h->d_items + ck.pf_lo.off, S);
+            ++launches;
         }
         tick(4);
         const size_t fin_smem = FIN_SMEM;

@@ -1495,15 +1495,19 @@ __device__ __forceinline__ void pf_E(int kind, int bit, uint32_t hi, uint32_t lo
     for (int t = 0; t < 4; ++t) e[t] = yv[t] * (xa[t] - xv[t]);
 }
 
-#ifndef PF_ROWS_PER_WARP
-#define PF_ROWS_PER_WARP 4
-#endif
-constexpr int PF_RW = PF_ROWS_PER_WARP, PF_WARPS = NR / PF_RW, PF_HB = 4;   // table rows per warp, warps per CTA, hi per k_pf_hi item
-// item: a = block of 128 lo, b = hi slice
-__global__ void __launch_bounds__(32 * PF_WARPS, 3)
-k_pf_lo(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, double* __restrict__ S)
+constexpr int PF_RW = 4, PF_WARPS = NR / PF_RW, PF_HBATCH = 4;   // table rows per warp, warps per CTA, hi per reduction round
+// Both weighted marginals in ONE pass over the lattice (round 2; before, k_pf_lo and k_pf_hi each re-read x, y and every
+// lattice neighbour).  CTA = a block of 128 lo x a slice of hi; lane = four consecutive lo, warp = PF_RW table rows:
+//   H1: the lane keeps acc[row][lo] over the hi of the slice -> partial table of the slice (as before)
+//   H2: per hi the lane's  sum_t T1[row][lo+t] E(hi, lo+t)  is parked in shared memory, PF_HBATCH hi at a time, and
+//       summed over the 32 lanes by one lane per (row, hi) in a fixed order -> partial table of this lo block
+// k_finish adds the slices / the lo blocks.   item: a = block of 128 lo, b = hi slice
+// Output (stP): slices x (NR + KA) x N1 partial H1 tables, then max(1, N1/128) x (NR + KA) x N2 partial H2 tables.
+__global__ void __launch_bounds__(32 * PF_WARPS, 2)
+k_pf(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, double* __restrict__ S)
 {
     __shared__ PfRows rows;
+    __shared__ double red[PF_WARPS][PF_RW * PF_HBATCH][33];
     const Item it = items[blockIdx.x];
     const SpaceDev& sp = spaces[it.space];
     pf_rows_build(rows, sp, threadIdx.x);
@@ -1512,113 +1516,68 @@ k_pf_lo(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, dou
     const uint32_t N1 = 1u << K1, N2 = 1u << K2;
     const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
     const uint32_t lo0 = (it.a << 7) | ((uint32_t)lane << 2);
-    if (lo0 >= N1) return;
+    const bool live = lo0 < N1;                           // narrow low parts leave lanes without columns
     const uint32_t per = (N2 + sp.slices - 1) / sp.slices;
     const uint32_t h0 = it.b * per, h1 = min(N2, h0 + per);
     const double* x = S + sp.x_off;
     const double* y = S + sp.y_off;
-    const double* T2 = S + sp.tabA + ((uint64_t)NR << K1);
+    const double* T1 = S + sp.tabA;
+    const double* T2 = T1 + ((uint64_t)NR << K1);
     int kind[PF_RW], bit[PF_RW];
+    double acc[PF_RW][4], tvr[PF_RW][4];
 #pragma unroll
-    for (int j = 0; j < PF_RW; ++j) { kind[j] = rows.kind[rg * PF_RW + j]; bit[j] = rows.bit[rg * PF_RW + j]; }
-    double acc[PF_RW][4];
+    for (int j = 0; j < PF_RW; ++j) {
+        kind[j] = live ? rows.kind[rg * PF_RW + j] : 0;
+        bit[j] = rows.bit[rg * PF_RW + j];
 #pragma unroll
-    for (int j = 0; j < PF_RW; ++j)
-#pragma unroll
-        for (int t = 0; t < 4; ++t) acc[j][t] = 0.0;
-    for (uint32_t hi = h0; hi < h1; ++hi) {
-        const uint64_t u0 = ((uint64_t)hi << K1) | lo0;
-        double xv[4], yv[4], ng[4];
-        ld4(x + u0, xv);
-        ld4(y + u0, yv);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) ng[t] = -(xv[t] * yv[t]);
-#pragma unroll
-        for (int j = 0; j < PF_RW; ++j) {
-            if (kind[j] == 0) continue;
-            double e[4];
-            bool zero;
-            pf_E(kind[j], bit[j], hi, lo0, K1, x, xv, yv, ng, e, zero);
-            if (zero) continue;
-            const double tw = T2[((uint64_t)(rg * PF_RW + j) << K2) + hi];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) acc[j][t] = fma(tw, e[t], acc[j][t]);
-        }
+        for (int t = 0; t < 4; ++t) { acc[j][t] = 0.0; tvr[j][t] = 0.0; }
+        if (kind[j] != 0) ld4(T1 + ((uint64_t)(rg * PF_RW + j) << K1) + lo0, tvr[j]);
     }
+    double* out2 = S + sp.stP + (uint64_t)sp.slices * (NR + KA) * N1 + (uint64_t)it.a * (NR + KA) * N2;
+    for (uint32_t hb = h0; hb < h1; hb += PF_HBATCH) {
+#pragma unroll
+        for (int hh = 0; hh < PF_HBATCH; ++hh) {
+            const uint32_t hi = hb + hh;
+            double p[PF_RW];
+#pragma unroll
+            for (int j = 0; j < PF_RW; ++j) p[j] = 0.0;
+            if (live && hi < h1) {
+                const uint64_t u0 = ((uint64_t)hi << K1) | lo0;
+                double xv[4], yv[4], ng[4];
+                ld4(x + u0, xv);
+                ld4(y + u0, yv);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) ng[t] = -(xv[t] * yv[t]);
+#pragma unroll
+                for (int j = 0; j < PF_RW; ++j) {
+                    if (kind[j] == 0) continue;
+                    double e[4];
+                    bool zero;
+                    pf_E(kind[j], bit[j], hi, lo0, K1, x, xv, yv, ng, e, zero);
+                    if (zero) continue;
+                    const double tw = T2[((uint64_t)(rg * PF_RW + j) << K2) + hi];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) acc[j][t] = fma(tw, e[t], acc[j][t]);
+                    p[j] = fma(tvr[j][3], e[3], fma(tvr[j][2], e[2], fma(tvr[j][1], e[1], tvr[j][0] * e[0])));
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < PF_RW; ++j) red[rg][j * PF_HBATCH + hh][lane] = p[j];
+        }
+        __syncwarp();
+        if (lane < PF_RW * PF_HBATCH) {
+            double s = 0.0;
+#pragma unroll
+            for (int l = 0; l < 32; ++l) s += red[rg][lane][l];
+            const int j = lane / PF_HBATCH, hh = lane % PF_HBATCH;
+            if (hb + hh < h1) out2[(uint64_t)(rg * PF_RW + j) * N2 + hb + hh] = s;
+        }
+        __syncwarp();
+    }
+    if (!live) return;
     double* out = S + sp.stP + (uint64_t)it.b * (NR + KA) * N1;
 #pragma unroll
     for (int j = 0; j < PF_RW; ++j) st4(out + (uint64_t)(rg * PF_RW + j) * N1 + lo0, acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
-}
-
-// item: a = block of PF_HB hi
-__global__ void __launch_bounds__(32 * PF_WARPS, 2)
-k_pf_hi(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, double* __restrict__ S)
-{
-    __shared__ PfRows rows;
-    __shared__ double red[PF_WARPS][PF_RW * PF_HB][33];
-    const Item it = items[blockIdx.x];
-    const SpaceDev& sp = spaces[it.space];
-    pf_rows_build(rows, sp, threadIdx.x);
-    __syncthreads();
-    const int KA = sp.KA, K1 = sp.splitA, K2 = KA - K1;
-    const uint32_t N1 = 1u << K1, N2 = 1u << K2;
-    const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
-    const uint32_t hb = it.a * PF_HB;
-    const double* x = S + sp.x_off;
-    const double* y = S + sp.y_off;
-    const double* T1 = S + sp.tabA;
-    int kind[PF_RW], bit[PF_RW];
-#pragma unroll
-    for (int j = 0; j < PF_RW; ++j) { kind[j] = rows.kind[rg * PF_RW + j]; bit[j] = rows.bit[rg * PF_RW + j]; }
-    double acc[PF_RW][PF_HB];
-#pragma unroll
-    for (int j = 0; j < PF_RW; ++j)
-#pragma unroll
-        for (int h = 0; h < PF_HB; ++h) acc[j][h] = 0.0;
-    for (uint32_t lo0 = (uint32_t)lane << 2; lo0 < N1; lo0 += 128) {
-        double tvr[PF_RW][4];                            // T1 rows of this warp at the lane's columns: shared by the PF_HB hi
-#pragma unroll
-        for (int j = 0; j < PF_RW; ++j) {
-            if (kind[j] != 0) ld4(T1 + ((uint64_t)(rg * PF_RW + j) << K1) + lo0, tvr[j]);
-            else {
-#pragma unroll
-                for (int t = 0; t < 4; ++t) tvr[j][t] = 0.0;
-            }
-        }
-#pragma unroll
-        for (int h = 0; h < PF_HB; ++h) {
-            const uint32_t hi = hb + h;
-            if (hi >= N2) continue;
-            const uint64_t u0 = ((uint64_t)hi << K1) | lo0;
-            double xv[4], yv[4], ng[4];
-            ld4(x + u0, xv);
-            ld4(y + u0, yv);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) ng[t] = -(xv[t] * yv[t]);
-#pragma unroll
-            for (int j = 0; j < PF_RW; ++j) {
-                if (kind[j] == 0) continue;
-                double e[4];
-                bool zero;
-                pf_E(kind[j], bit[j], hi, lo0, K1, x, xv, yv, ng, e, zero);
-                if (zero) continue;
-                acc[j][h] = fma(tvr[j][3], e[3], fma(tvr[j][2], e[2], fma(tvr[j][1], e[1], fma(tvr[j][0], e[0], acc[j][h]))));
-            }
-        }
-    }
-    // sum over the lanes through shared memory: value q of lane l -> red[q][l]; lane q then adds row q
-#pragma unroll
-    for (int j = 0; j < PF_RW; ++j)
-#pragma unroll
-        for (int h = 0; h < PF_HB; ++h) red[rg][j * PF_HB + h][lane] = acc[j][h];
-    __syncwarp();
-    if (lane >= PF_RW * PF_HB) return;
-    double s = 0.0;
-#pragma unroll
-    for (int l = 0; l < 32; ++l) s += red[rg][lane][l];
-    const int j = lane / PF_HB, h = lane % PF_HB;
-    double* out = S + sp.stP + (uint64_t)sp.slices * (NR + KA) * N1;
-    if (hb + h < N2) out[(uint64_t)(rg * PF_RW + j) * N2 + hb + h] = s;
 }
 // ------------------------------------------------------------------------------------------
 // Gradient contraction.  For event row i and sub-state u of a group (i not in u)
@@ -1670,7 +1629,7 @@ k_finish(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, ui
             const Side sd = side_of(sp, g, S);
             const double* ptab = pmode == 2 ? sd.t + ((uint64_t)NR << K1) : sd.t;     // T1 or T2
             const double* pH = S + sp.stP + (pmode == 2 ? (uint64_t)sp.slices * (NR + sp.KA) * (1u << K1) : 0);
-            const int psl = pmode == 1 ? (int)sp.slices : 1;
+            const int psl = pmode == 1 ? (int)sp.slices : pmode == 2 ? (int)max(1u, (1u << K1) >> 7) : 1;   // hi slices / lo blocks of k_pf
             const uint64_t pslice = (uint64_t)(NR + sp.KA) * NG;
             const double* st = S + (g ? sp.stB : sp.stA);
             const double* y = S + sp.y_off;
@@ -1710,7 +1669,13 @@ k_finish(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, ui
                     if (uv && (rrow || rps)) {
                         if (pmode) {                              // weighted marginals from k_pf_lo / k_pf_hi
                             double hsum = 0.0;
-                            for (int q = 0; q < psl; ++q) hsum += pH[q * pslice + (uint64_t)r * NG + u];
+                            const double* ph = pH + (uint64_t)r * NG + u;
+                            int q = 0;
+                            for (; q + 4 <= psl; q += 4) {            // four loads in flight, added in slice order
+                                const double h0 = ph[q * pslice], h1 = ph[(q + 1) * pslice], h2 = ph[(q + 2) * pslice], h3 = ph[(q + 3) * pslice];
+                                hsum += h0; hsum += h1; hsum += h2; hsum += h3;
+                            }
+                            for (; q < psl; ++q) hsum += ph[q * pslice];
                             wv = ptab[(uint64_t)r * NG + u] * hsum;
                         } else {
                             const double R = rrow ? sd.rate(r, u) : sd.special(r, u);
