@@ -414,7 +414,7 @@ static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_da
         for (uint32_t i = 0; i < ck.nspaces; ++i)
             if (is_prod(sp[i])) {
                 const uint32_t nlo = std::max<uint32_t>(1u, (1u << sp[i].splitA) >> 7);
-                const uint32_t nhi = std::max<uint32_t>(1u, (1u << (sp[i].KA - sp[i].splitA)) >> 4);
+                const uint32_t nhi = std::max<uint32_t>(1u, (1u << (sp[i].KA - sp[i].splitA)) / DG_HIB);
                 for (uint32_t hb = 0; hb < nhi; ++hb)
                     for (uint32_t lb = 0; lb < nlo; ++lb) items.push_back({i, lb, hb});
             }

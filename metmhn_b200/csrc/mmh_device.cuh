@@ -1395,65 +1395,87 @@ __device__ __forceinline__ void pf_rows_build(PfRows& m, const SpaceDev& sp, int
 //   D[hi][lo] = d(u) + sum_{r not in u} T1[r][lo] T2[r][hi]
 // is a rank-(nrows+2) product once the rows of present events are masked on their own bit; d(u) is 1
 // (diagnosis_theta form, vanilla.py:269) or, for type 2, the two diagnosis-rate products held in rows 30/31.
-// CTA = 16 hi x 128 lo, thread = 2 hi x 4 lo.   item: a = lo block, b = hi block
+// A small FP64 matrix product [hi x rows] [rows x lo]: the masked factor tiles of the CTA (32 hi x 128 lo) are staged in
+// shared memory once, a thread owns 4 hi x 4 lo (16 accumulators, four 16-byte shared loads per 16 FMAs).
+// The lo tile is reused for up to DG_HIB / DG_HI hi tiles.   item: a = lo block of 128, b = hi block of DG_HIB
+constexpr int DG_HI = 32, DG_LO = 128, DG_HIB = 256;
 __global__ void __launch_bounds__(256)
 k_diag_prod(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, double* __restrict__ S)
 {
     __shared__ PfRows rows;
+    __shared__ __align__(16) double fa[NR][DG_LO];       // T1[r][lo], zero where the row does not count
+    __shared__ __align__(16) double fb[NR][DG_HI];       // T2[r][hi]
     const Item it = items[blockIdx.x];
     const SpaceDev& sp = spaces[it.space];
     pf_rows_build(rows, sp, threadIdx.x);
     __syncthreads();
     const int K1 = sp.splitA, K2 = sp.KA - K1;
     const uint32_t N1 = 1u << K1, N2 = 1u << K2;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint32_t lo0 = (it.a << 7) | ((uint32_t)lane << 2);
-    const uint32_t hi0 = (it.b << 4) | ((uint32_t)w << 1);
-    if (lo0 >= N1 || hi0 >= N2) return;
     const double* T1 = S + sp.tabA;
     const double* T2 = T1 + ((uint64_t)NR << K1);
     double* vec = S + sp.tabA + ((uint64_t)NR << K1) + ((uint64_t)NR << K2);
     const bool s2 = setup_sel(sp, 0).dg == 4;
-    double d[2][4];
-#pragma unroll
-    for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int t = 0; t < 4; ++t) d[h][t] = s2 ? 0.0 : 1.0;
-    for (int r = 0; r < NR; ++r) {
+    const uint32_t lob = it.a << 7;
+    // rows 0..28 are events; for type 2 the two diagnosis-rate products (rows 30 / 31) join the sum
+    for (int t = threadIdx.x; t < NR * DG_LO; t += blockDim.x) {
+        const int r = t >> 7;
+        const uint32_t lo = lob + ((uint32_t)t & (DG_LO - 1));
         const int kind = rows.kind[r];
-        if (kind == 0 || r >= ROW_D) continue;
-        double b[4];
-        ld4(T1 + ((uint64_t)r << K1) + lo0, b);
-        double a0 = T2[((uint64_t)r << K2) + hi0], a1 = T2[((uint64_t)r << K2) + hi0 + 1];
-        const int bit = rows.bit[r];
-        if (kind == 2) {
-#pragma unroll
-            for (int t = 0; t < 4; ++t) if (((lo0 + t) >> bit) & 1u) b[t] = 0.0;
-        } else if (kind == 3) {
-            if ((hi0 >> bit) & 1u) a0 = 0.0;
-            if (((hi0 + 1) >> bit) & 1u) a1 = 0.0;
-        }
-#pragma unroll
-        for (int t = 0; t < 4; ++t) { d[0][t] = fma(a0, b[t], d[0][t]); d[1][t] = fma(a1, b[t], d[1][t]); }
+        double v = 0.0;
+        const bool use = (r < ROW_D && kind != 0) || (s2 && r >= ROW_DP);
+        if (use && lo < N1 && !(kind == 2 && r < ROW_D && ((lo >> rows.bit[r]) & 1u))) v = T1[((uint64_t)r << K1) + lo];
+        fa[r][t & (DG_LO - 1)] = v;
     }
+    const int tl = threadIdx.x & 31, th = threadIdx.x >> 5;            // 32 column groups x 8 row groups
+    const uint32_t lo0 = lob + ((uint32_t)tl << 2);
     const uint64_t NG = (uint64_t)N1 << K2;
-    if (s2) {
-        double bp[4], bm[4];
-        ld4(T1 + ((uint64_t)ROW_DP << K1) + lo0, bp);
-        ld4(T1 + ((uint64_t)ROW_DM << K1) + lo0, bm);
+    for (uint32_t hib = it.b * DG_HIB; hib < min(N2, (it.b + 1u) * DG_HIB); hib += DG_HI) {
+        __syncthreads();                                               // the previous hi tile is consumed; (first) fa is in place
+        for (int t = threadIdx.x; t < NR * DG_HI; t += blockDim.x) {
+            const int r = t >> 5;
+            const uint32_t hi = hib + ((uint32_t)t & (DG_HI - 1));
+            const int kind = rows.kind[r];
+            double v = 0.0;
+            const bool use = (r < ROW_D && kind != 0) || (s2 && r >= ROW_DP);
+            if (use && hi < N2 && !(kind == 3 && r < ROW_D && ((hi >> rows.bit[r]) & 1u))) v = T2[((uint64_t)r << K2) + hi];
+            fb[r][t & (DG_HI - 1)] = v;
+        }
+        __syncthreads();
+        const uint32_t hi0 = hib + ((uint32_t)th << 2);
+        double d[4][4];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const double ap = T2[((uint64_t)ROW_DP << K2) + hi0 + h], am = T2[((uint64_t)ROW_DM << K2) + hi0 + h];
+        for (int h = 0; h < 4; ++h)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) d[h][t] = s2 ? 0.0 : 1.0;
+#pragma unroll 4
+        for (int r = 0; r < ROW_D; ++r) {
+            const double2 b01 = *reinterpret_cast<const double2*>(&fa[r][tl << 2]), b23 = *reinterpret_cast<const double2*>(&fa[r][(tl << 2) + 2]);
+            const double2 a01 = *reinterpret_cast<const double2*>(&fb[r][th << 2]), a23 = *reinterpret_cast<const double2*>(&fb[r][(th << 2) + 2]);
+            const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+            for (int h = 0; h < 4; ++h)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) d[h][t] = fma(a[h], b[t], d[h][t]);
+        }
+        if (lo0 >= N1) continue;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            if (hi0 + h >= N2) break;
             const uint64_t u0 = ((uint64_t)(hi0 + h) << K1) | lo0;
-            double vp[4], vm[4];
+            if (s2) {
+                double vp[4], vm[4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) { vp[t] = ap * bp[t]; vm[t] = am * bm[t]; d[h][t] += vp[t] + vm[t]; }
-            st4(vec + NG + u0, vp[0], vp[1], vp[2], vp[3]);
-            st4(vec + 2 * NG + u0, vm[0], vm[1], vm[2], vm[3]);
+                for (int t = 0; t < 4; ++t) {
+                    vp[t] = fb[ROW_DP][(th << 2) + h] * fa[ROW_DP][(tl << 2) + t];
+                    vm[t] = fb[ROW_DM][(th << 2) + h] * fa[ROW_DM][(tl << 2) + t];
+                    d[h][t] += vp[t] + vm[t];
+                }
+                st4(vec + NG + u0, vp[0], vp[1], vp[2], vp[3]);
+                st4(vec + 2 * NG + u0, vm[0], vm[1], vm[2], vm[3]);
+            }
+            st4(vec + u0, d[h][0], d[h][1], d[h][2], d[h][3]);
         }
     }
-#pragma unroll
-    for (int h = 0; h < 2; ++h) st4(vec + (((uint64_t)(hi0 + h) << K1) | lo0), d[h][0], d[h][1], d[h][2], d[h][3]);
 }
 
 // Weighted marginals of a product-form space.  With x the adjoint and y the forward vector, row r of the gradient
@@ -1503,7 +1525,10 @@ constexpr int PF_RW = 4, PF_WARPS = NR / PF_RW, PF_HBATCH = 4;   // table rows p
 //       summed over the 32 lanes by one lane per (row, hi) in a fixed order -> partial table of this lo block
 // k_finish adds the slices / the lo blocks.   item: a = block of 128 lo, b = hi slice
 // Output (stP): slices x (NR + KA) x N1 partial H1 tables, then max(1, N1/128) x (NR + KA) x N2 partial H2 tables.
-__global__ void __launch_bounds__(32 * PF_WARPS, 2)
+#ifndef PF_CTAS
+#define PF_CTAS 2
+#endif
+__global__ void __launch_bounds__(32 * PF_WARPS, PF_CTAS)
 k_pf(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, double* __restrict__ S)
 {
     __shared__ PfRows rows;
@@ -1533,6 +1558,7 @@ k_pf(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, double
         for (int t = 0; t < 4; ++t) { acc[j][t] = 0.0; tvr[j][t] = 0.0; }
         if (kind[j] != 0) ld4(T1 + ((uint64_t)(rg * PF_RW + j) << K1) + lo0, tvr[j]);
     }
+    const bool any_row = (kind[0] | kind[1] | kind[2] | kind[3]) != 0;     // warps without a live row skip the loads
     double* out2 = S + sp.stP + (uint64_t)sp.slices * (NR + KA) * N1 + (uint64_t)it.a * (NR + KA) * N2;
     for (uint32_t hb = h0; hb < h1; hb += PF_HBATCH) {
 #pragma unroll
@@ -1541,7 +1567,7 @@ k_pf(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, double
             double p[PF_RW];
 #pragma unroll
             for (int j = 0; j < PF_RW; ++j) p[j] = 0.0;
-            if (live && hi < h1) {
+            if (any_row && hi < h1) {
                 const uint64_t u0 = ((uint64_t)hi << K1) | lo0;
                 double xv[4], yv[4], ng[4];
                 ld4(x + u0, xv);
