@@ -1398,7 +1398,7 @@ __device__ __forceinline__ void pf_rows_build(PfRows& m, const SpaceDev& sp, int
 // A small FP64 matrix product [hi x rows] [rows x lo]: the masked factor tiles of the CTA (32 hi x 128 lo) are staged in
 // shared memory once, a thread owns 4 hi x 4 lo (16 accumulators, four 16-byte shared loads per 16 FMAs).
 // The lo tile is reused for up to DG_HIB / DG_HI hi tiles.   item: a = lo block of 128, b = hi block of DG_HIB
-constexpr int DG_HI = 32, DG_LO = 128, DG_HIB = 256;
+constexpr int DG_HI = 32, DG_LO = 128, DG_HIB = 64;
 __global__ void __launch_bounds__(256)
 k_diag_prod(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, double* __restrict__ S)
 {
