@@ -375,7 +375,7 @@ def run_ours(args, rank, local_rank, world):
     kernels = {"setup": "k_setup, k_setup_wide, k_diag_prod",
                "solve_fwd": "k_solve_tile<fwd> (+ k_solve_big4 / k_solve_small* for the generic and small tiers)",
                "solve_adj": "k_solve_tile_adjb / k_solve_tile<adj> (+ k_solve_big4 / k_solve_small*)",
-               "contraction": "k_stats_a/b, k_pf_lo/hi, k_finish"}
+               "contraction": "k_stats_a/b, k_pf, k_finish"}
     # DRAM traffic of the tile solve kernels from the committed ncu capture (profiles/r1_final_solve_tile_ncu_full.txt,
     # 24 consecutive level launches of one chunk of 2^22..2^23-state pairs): forward 12.9 bytes per state (read +
     # write) against 8 algorithmic; adjoint with fused group-B statistics 16.9 (it also reads y)
