@@ -376,10 +376,10 @@ def run_ours(args, rank, local_rank, world):
                "solve_fwd": "k_solve_tile<fwd> (+ k_solve_big4 / k_solve_small* for the generic and small tiers)",
                "solve_adj": "k_solve_tile_adjb / k_solve_tile<adj> (+ k_solve_big4 / k_solve_small*)",
                "contraction": "k_stats_a/b, k_pf, k_finish"}
-    # DRAM traffic of the tile solve kernels from the committed ncu capture (profiles/r1_final_solve_tile_ncu_full.txt,
-    # 24 consecutive level launches of one chunk of 2^22..2^23-state pairs): forward 12.9 bytes per state (read +
-    # write) against 8 algorithmic; adjoint with fused group-B statistics 16.9 (it also reads y)
-    traffic_per_state = {"solve_fwd": 12.9, "solve_adj": 16.9}
+    # DRAM traffic of the tile solve kernels from the committed ncu capture (profiles/r2_final_solve_tile_ncu_full.txt,
+    # 24 consecutive level launches of one chunk of 2^22..2^23-state pairs): forward 13.0 bytes per state (read +
+    # write) against 8 algorithmic; adjoint with fused group-B statistics 17.6 (it also reads y)
+    traffic_per_state = {"solve_fwd": 13.0, "solve_adj": 17.6}
     # the dominant KERNEL is the tile solve (forward and adjoint instantiations); the contraction class is several
     # kernels, each smaller
     dominant = "solve_adj" if cls["solve_adj"] >= cls["solve_fwd"] else "solve_fwd"
@@ -421,9 +421,9 @@ def run_ours(args, rank, local_rank, world):
                                  "(chunks serialised on one stream); the timed steps overlap chunks on side streams",
                          "binding_resource": {
                              "what": "random 128-byte line reads through L2 (every state reads ~K/2 finished neighbours)",
-                             "kernel_L2_sector_traffic_TBs": [6.0, 6.4], "kernel_L2_hit_rate": 0.6,
+                             "kernel_L2_sector_traffic_TBs": [5.8, 7.7], "kernel_L2_hit_rate": 0.6,
                              "ceiling_TBs": {"lines_in_L2_24_warps_per_SM": 6.7, "lines_in_HBM_24_warps_per_SM": 4.0},
-                             "source": "profiles/r1_final_solve_tile_ncu_full.txt, profiles/r1_microbench_line_reads.txt "
+                             "source": "profiles/r2_final_solve_tile_ncu_full.txt, profiles/r1_microbench_line_reads.txt "
                                        "(scripts/microbench/line_reads.cu); measured once per round, not in this run"}},
             "roofline_step": {"hbm": {"achieved_GBs": st["alg_bytes"] / t_rank / 1e9, "peak_GBs": peaks["hbm_gbs"], "frac": hbm_frac},
                               "fp64": {"achieved_TFLOPs": st["alg_flops"] / t_rank / 1e12, "peak_TFLOPs": fp64_peak,
