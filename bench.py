@@ -310,7 +310,8 @@ def run_ours(args, rank, local_rank, world):
     d = workload(args)
     dat, ep = d["dat"], d["eval_point"]
     t0 = time.perf_counter()
-    ev = ShardedEvaluator(dat, rank=rank, world=world, device=local_rank, chunk_bytes=args.chunk_bytes)
+    ev = ShardedEvaluator(dat, rank=rank, world=world, device=local_rank, chunk_bytes=args.chunk_bytes,
+                          rebalance=args.rebalance)
     setup_s = time.perf_counter() - t0
     w0, w1 = class_weights(ev.n_dat, ev.n_em, PERC_MET)
     par, out = ev.device_buffers()
@@ -398,6 +399,10 @@ def run_ours(args, rank, local_rank, world):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(base_config(args),
                        parallelism=f"patients sharded over {world} GPU(s) by LPT cost model + 1 all-reduce",
+                       partition_rebalance={"rounds_allowed": args.rebalance if world > 1 else 0,
+                                            "shard_ms_per_round": ev.rebalance_log,
+                                            "what": "at construction (outside the timed region) every rank times its shard and "
+                                                    "the rows are dealt again with capacities proportional to the measured speed"},
                        dataset_resident=True, dataset_upload_and_plan_s=round(setup_s, 3),
                        l2_policy="working set per step (x, y vectors of every patient, "
                                  f"{32.0 * states / 2 ** 30:.1f} GiB algorithmic) exceeds the 126 MB L2; no flush needed",
@@ -459,6 +464,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--ref-step-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--rebalance", type=int, default=3, help="measured-cost rebalancing rounds of the partition (N > 1)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

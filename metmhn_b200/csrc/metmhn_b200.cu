@@ -1139,16 +1139,20 @@ struct mmh_multi {
     int64_t n_dat = 0, n_em = 0;
 };
 
-// work estimate of a row: lattice states times (bits + 8), summed over the row's spaces (metmhn_b200/sharded.py)
+// work estimate of a row: lattice states times the measured cost per state (ps, B200) of the row's kind and size tier --
+// the table of metmhn_b200/sharded.py (scripts/calibrate_cost.py)
 static double row_cost(const int8_t* row, int n)
 {
     int pt = 0, mt = 0;
     for (int e = 0; e < n; ++e) { pt += row[2 * e] != 0; mt += row[2 * e + 1] != 0; }
     const int seed = row[2 * n] != 0, typ = row[2 * n + 2];
-    auto c = [](int k) { return std::ldexp(1.0, k) * (k + 8); };
-    if (typ == 0 || typ == 1) return c(pt + seed);
-    if (typ == 2) return c(mt + 1);
-    if (typ == 3) return c(pt + mt) + c(pt) + c(mt);
+    auto single = [](int k) { return std::ldexp(1.0, k) * (k >= 17 ? 85.0 : k >= 13 ? 112.0 : k >= 9 ? 232.0 : 800.0); };
+    // pairs with fewer than 4 PT events or a tumour with more than 16 take the generic solve kernel
+    const bool generic = pt < 4 || pt > 16 || mt > 16;
+    auto pair = [generic](int k) { return std::ldexp(1.0, k) * (k < 13 ? 485.0 : generic ? (k >= 20 ? 195.0 : 590.0) : (k >= 20 ? 37.0 : 66.0)); };
+    if (typ == 0 || typ == 1) return single(pt + seed);
+    if (typ == 2) return single(mt + 1);
+    if (typ == 3) return pair(pt + mt);
     return 1.0;
 }
 

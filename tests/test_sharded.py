@@ -6,7 +6,7 @@ import socket
 import numpy as np
 import pytest
 
-from metmhn_b200.sharded import ShardedEvaluator, class_weights, partition, patient_cost
+from metmhn_b200.sharded import ShardedEvaluator, class_weights, partition, patient_cost, rebalance_moves
 from metmhn_b200.simulate import syn_v1
 
 
@@ -21,6 +21,27 @@ def test_partition_is_balanced_and_complete():
         # LPT guarantee: max load <= mean + largest item
         assert loads.max() <= loads.mean() + cost.max() + 1e-9
     assert np.array_equal(partition(dat, 4), partition(dat, 4))      # deterministic
+    # capacities (measured-cost rebalancing): the loads follow the requested shares
+    a = partition(dat, 3, capacity=[0.5, 0.3, 0.2])
+    cost = patient_cost(dat)
+    loads = np.array([cost[a == r].sum() for r in range(3)])
+    assert np.allclose(loads / loads.sum(), [0.5, 0.3, 0.2], atol=0.02)
+
+
+def test_rebalance_moves_shift_load_from_slow_to_fast_ranks():
+    d = syn_v1(12, 2000, 12)
+    dat = d["dat"]
+    cost = patient_cost(dat)
+    a0 = partition(dat, 4)
+    load0 = np.array([cost[a0 == r].sum() for r in range(4)])
+    times = np.array([1.10, 1.00, 0.95, 0.95])                     # rank 0 measured 10 % slow
+    a1 = rebalance_moves(a0, cost, times, damping=1.0)
+    load1 = np.array([cost[a1 == r].sum() for r in range(4)])
+    assert load1[0] < load0[0] and load1[2] > load0[2] and load1[3] > load0[3]
+    want = load0 * times.mean() / times
+    assert np.allclose(load1 / load1.sum(), want / want.sum(), atol=0.02)
+    assert np.array_equal(a1, rebalance_moves(a0, cost, times, damping=1.0))           # deterministic
+    assert np.array_equal(rebalance_moves(a0, cost, np.ones(4)), a0)                   # balanced: nothing moves
 
 
 def test_class_weights_match_reference_formula():
