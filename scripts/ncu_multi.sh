@@ -3,4 +3,4 @@ export MMH_GRAPH=0 MMH_STREAMS=1 EVALS=1 VALUE_ONLY=0
 cap() { # name regex skip count
   ncu --set full --import-source on --clock-control none -k "regex:$2" -s $3 -c $4 -o gpurun_out/p14_$1 -f python scripts/quick_time.py 25 100000 > gpurun_out/p14_$1.log 2>&1
 }
-cap pf 'k_pf_lo|k_pf_hi|k_diag_prod' 6 3
+cap pf 'k_pf|k_diag_prod' 6 3
