@@ -48,6 +48,7 @@ struct ChunkPlan {
     std::vector<Range> main_lvt, sec_lvt;        // big-tier tiles per level (tiled kernel)
     std::vector<Range> main_lvt_adj, main_lvt_adjb;  // adjoint pass of the main tiled spaces: plain / with fused B statistics
     std::vector<Range> main_rb;                  // row-block kernel: blocks per OUTER level (both passes)
+    std::vector<Range> main_lvw;                 // pairs with a wide PT group: tiles per level (both passes, k_solve_tile_w)
     uint64_t scratch = 0;                        // doubles
 };
 
@@ -422,9 +423,12 @@ static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_da
         // spaces the tiled solve kernel takes (must agree with tiled_space() on the device side)
         auto tiled = [&](const SpaceDev& s) {
             if (bits(s) < BIGK || s.kind == K_PRE || rb_space(s)) return false;
-            if (s.kind == K_JOINT) return !s.splitA && !s.splitB && s.KA >= 4;
+            static const bool wide_on = [] { const char* e = std::getenv("MMH_WIDE_TILE"); return !e || std::atoi(e) != 0; }();
+            if (s.kind == K_JOINT) return !s.splitB && (s.splitA ? (wide_on && s.splitA >= 4) : s.KA >= 4);
             return s.splitA >= 4;
         };
+        // pairs with a wide PT group: cut like a product space (k_solve_tile_w, TM_WIDE in mmh_device.cuh)
+        auto wide_t = [&](const SpaceDev& s) { return s.kind == K_JOINT && s.splitA != 0 && tiled(s); };
         auto levels_of = [&](auto pred, std::vector<Range>& lv) {
             int maxkh = -1;
             for (uint32_t i = 0; i < ck.nspaces; ++i) if (pred(sp[i]) && bits(sp[i]) >= BIGK && !tiled(sp[i]) && !rb_space(sp[i])) maxkh = std::max(maxkh, bits(sp[i]) - 7);
@@ -449,7 +453,8 @@ static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_da
         auto levels_of_t = [&](auto pred, std::vector<Range>& lv) {
             int maxl = -1;
             auto dims = [&](const SpaceDev& s, int& kbA, int& kbB) {
-                if (s.kind == K_JOINT) { kbA = s.KA - 4; kbB = s.KB; }
+                if (s.kind == K_JOINT && s.splitA) { kbA = s.splitA - 4; kbB = s.KB + s.KA - s.splitA; }
+                else if (s.kind == K_JOINT) { kbA = s.KA - 4; kbB = s.KB; }
                 else { kbA = s.splitA - 4; kbB = s.KA - s.splitA; }
             };
             for (uint32_t i = 0; i < ck.nspaces; ++i)
@@ -544,8 +549,9 @@ static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_da
         }
         levels_of(is_main, ck.main_lv);
         levels_of(is_sec, ck.sec_lv);
-        levels_of_t(is_main, ck.main_lvt);
-        levels_of_t([&](const SpaceDev& s) { return is_main(s) && !fused_b(s); }, ck.main_lvt_adj);
+        levels_of_t([&](const SpaceDev& s) { return is_main(s) && !wide_t(s); }, ck.main_lvt);
+        levels_of_t([&](const SpaceDev& s) { return is_main(s) && !fused_b(s) && !wide_t(s); }, ck.main_lvt_adj);
+        levels_of_t(wide_t, ck.main_lvw);
         levels_of_adjb(ck.main_lvt_adjb);
         levels_of_t(is_sec, ck.sec_lvt);
         ck.st_a.off = items.size();
@@ -743,6 +749,16 @@ static int enqueue_eval(mmh_handle* h, const double* d_params, double w0, double
                 ++launches;
             }
         };
+        auto bigw = [&](bool adj) {
+            const int L = (int)ck.main_lvw.size();
+            for (int q = 0; q < L; ++q) {
+                const Range& r = ck.main_lvw[adj ? L - 1 - q : q];
+                if (!r.cnt) continue;
+                if (adj) k_solve_tile_w<true><<<r.cnt, 256, 0, st>>>(sp, h->d_items + r.off, h->d_hs, h->d_hsidx, S);
+                else     k_solve_tile_w<false><<<r.cnt, 256, 0, st>>>(sp, h->d_items + r.off, h->d_hs, h->d_hsidx, S);
+                ++launches;
+            }
+        };
         auto rowblk = [&](bool adj) {
             const int L = (int)ck.main_rb.size();
             for (int q = 0; q < L; ++q) {
@@ -761,7 +777,7 @@ static int enqueue_eval(mmh_handle* h, const double* d_params, double w0, double
         tick(1);
         small(ck.pre, false); small4(ck.pre4, false);
         small(ck.main_small, false); small4(ck.main_small4, false);
-        big(ck.main_lv, false); bigt(ck.main_lvt, false); rowblk(false);
+        big(ck.main_lv, false); bigt(ck.main_lvt, false); bigw(false); rowblk(false);
         small(ck.sec_small, false); small4(ck.sec_small4, false);
         big(ck.sec_lv, false); bigt(ck.sec_lvt, false);
         tick(5);
@@ -778,7 +794,7 @@ static int enqueue_eval(mmh_handle* h, const double* d_params, double w0, double
         }
         tick(2);
         small(ck.main_small, true); small4(ck.main_small4, true);
-        big(ck.main_lv, true); bigt(ck.main_lvt_adj, true);
+        big(ck.main_lv, true); bigt(ck.main_lvt_adj, true); bigw(true);
         for (int q = (int)ck.main_lvt_adjb.size() - 1; q >= 0; --q) {
             const Range& r = ck.main_lvt_adjb[q];
             if (!r.cnt) continue;

@@ -717,13 +717,33 @@ struct TileCtx {
     const double* dB;                  // pair: B part of the diagonal
     int KC, KR;
 };
+// wide pair (TM_WIDE): the row index is (uB << K2A | high part of uA); which part of it a factor table is indexed by
+struct TileCtxW : TileCtx {
+    uint32_t mH;                       // mask of the high part of uA inside the row index
+    uint32_t mAfull;                   // 2^KA - 1
+    int K2A;
+    uint8_t rsh[MAXG];                 // row bit b: index of rowB[b] = (row >> rsh[b]) & rmask[b]
+    uint32_t rmask[MAXG];
+    uint8_t cfone[MAXG];               // row bit b has no column factor (an MT event: scalar rate per row)
+};
+
+// Table modes of the tile kernels.  TM_PAIR: a pair whose groups have at most MAXT bits (one plain table per group, an A
+// edge's rate is a column vector, a B edge's rate one scalar per row).  TM_PROD: a product-form single-tumour space
+// (rate = column factor T1[ev][lo] x row factor T2[ev][hi], full diagonal vector).  TM_WIDE: a pair whose PT group has more
+// than MAXT bits, e.g. 18 PT events against 5 MT events: its A rates are stored in product form too, so the lattice is cut
+// like a product space -- columns = the low K1A bits of uA, rows = (uB, high part of uA) -- which gives every level enough
+// rows to fill the 8-row tiles however few MT events there are; MT edges are row edges with a scalar rate and no column
+// factor, the diagonal is dA[uA] (full vector) + dB[uB].  Before, these pairs ran on the generic kernel: 60 such pairs were
+// 31 % of the n = 20 / 10 000 step, 28 were 7 % of the n = 25 / 100 000 step (scripts/marginal_generic.py).
+constexpr int TM_PAIR = 0, TM_PROD = 1, TM_WIDE = 2;
 
 __device__ __forceinline__ bool tiled_space(const SpaceDev& sp)
 {
     if ((int)sp.KA + (int)sp.KB < BIGK || sp.kind == K_PRE) return false;
-    if (sp.kind == K_JOINT) return !sp.splitA && !sp.splitB && sp.KA >= 4;
+    if (sp.kind == K_JOINT) return !sp.splitB && (sp.splitA ? sp.splitA >= 4 : sp.KA >= 4);
     return sp.splitA >= 4;
 }
+__device__ __forceinline__ bool wide_tiled_space(const SpaceDev& sp) { return sp.kind == K_JOINT && sp.splitA != 0; }
 
 __device__ __forceinline__ void tile_ctx_build(TileCtx& c, const SpaceDev& sp, const double* __restrict__ S, int t)
 {
@@ -746,6 +766,29 @@ __device__ __forceinline__ void tile_ctx_build(TileCtx& c, const SpaceDev& sp, c
     }
 }
 
+__device__ __forceinline__ void tile_ctx_build_wide(TileCtxW& c, const SpaceDev& sp, const double* __restrict__ S, int t)
+{
+    {
+        const int KA = sp.KA, KB = sp.KB, K1 = sp.splitA, K2 = KA - K1;
+        const double* T1 = S + sp.tabA;
+        const double* T2 = T1 + ((uint64_t)NR << K1);
+        if (t < K1) { c.colA[t] = T1 + ((uint64_t)sp.evA[t] << K1); c.rowA[t] = T2 + ((uint64_t)sp.evA[t] << K2); }
+        if (t < K2) {
+            c.rowB[t] = T2 + ((uint64_t)sp.evA[K1 + t] << K2); c.colB[t] = T1 + ((uint64_t)sp.evA[K1 + t] << K1);
+            c.rsh[t] = 0; c.rmask[t] = (1u << K2) - 1u; c.cfone[t] = 0;
+        }
+        if (t < KB) {
+            c.rowB[K2 + t] = S + sp.tabB + ((uint64_t)sp.evB[t] << KB); c.colB[K2 + t] = &c_one;
+            c.rsh[K2 + t] = (uint8_t)K2; c.rmask[K2 + t] = (1u << KB) - 1u; c.cfone[K2 + t] = 1;
+        }
+        if (t == 0) {
+            c.dA = T2 + ((uint64_t)NR << K2);                 // full vector of the A part of the diagonal (Side::special)
+            c.dB = S + sp.tabB + ((uint64_t)ROW_D << KB);
+            c.KC = K1; c.KR = KB + K2; c.K2A = K2; c.mH = (1u << K2) - 1u; c.mAfull = (1u << KA) - 1u;
+        }
+    }
+}
+
 // 32-byte global load / store (LDG.E.256 / STG.E.256 on sm_100a): four lanes cover one 128-byte line with a single
 // request, which halves the L1 wavefronts of the tile kernels against two 16-byte loads per lane.
 __device__ __forceinline__ void ld4(const double* __restrict__ p, double (&f)[4])
@@ -757,16 +800,22 @@ __device__ __forceinline__ void st4(double* __restrict__ p, double a, double b, 
     asm volatile("st.global.v4.f64 [%4], {%0,%1,%2,%3};" :: "d"(a), "d"(b), "d"(c), "d"(d), "l"(p) : "memory");
 }
 
-// right-hand side of the four states of a lane: non-zero on few states only (except the second phase's start vector)
-template <bool ADJ>
+// right-hand side of the four states of a lane: non-zero on few states only (except the second phase's start vector).
+// WIDEJ (TM_WIDE): the tile's columns are only the low part of group A, (uB, uA) come from the state index with jKA / jKB.
+template <bool ADJ, bool WIDEJ = false>
 __device__ __forceinline__ void tile_rhs(const SpaceDev& sp, const SpaceDev* __restrict__ spaces, const double* __restrict__ S,
-                                         int KC, int KR, uint32_t row, uint32_t lo0, double (&acc)[4])
+                                         int KC, int KR, uint32_t row, uint32_t lo0, double (&acc)[4], int jKA = 0, int jKB = 0)
 {
     const uint32_t s0 = (row << KC) | lo0;
     {
         const uint32_t NC = 1u << KC, NRW = 1u << KR;
         bool any;
-        if (!ADJ) {
+        if (WIDEJ) {
+            const uint32_t NA = 1u << jKA, NB = 1u << jKB;
+            const uint32_t uA = s0 & (NA - 1u), uB = s0 >> jKA;
+            if (!ADJ) any = uB < (1u << sp.nb) && ((uB ^ uA) & ~3u) == 0u;
+            else any = (sp.has_pf && (uA | 3u) == NA - 1u) || (sp.has_mf && uB == NB - 1u);
+        } else if (!ADJ) {
             if (sp.kind == K_JOINT) any = row < (1u << sp.nb) && ((row ^ lo0) & ~3u) == 0u;
             else if (sp.kind == K_PF || sp.kind == K_MF) any = true;
             else any = s0 == 0u;
@@ -782,8 +831,8 @@ __device__ __forceinline__ void tile_rhs(const SpaceDev& sp, const SpaceDev* __r
 }
 
 // edges on the row bits of a lane's four states (sources in global memory): acc += rate * v[other row]
-template <bool ADJ, bool PROD>
-__device__ __forceinline__ void tile_row_edges(const TileCtx& c, const double* __restrict__ v, uint32_t row, uint32_t lo0,
+template <bool ADJ, int MODE, class CTX>
+__device__ __forceinline__ void tile_row_edges(const CTX& c, const double* __restrict__ v, uint32_t row, uint32_t lo0,
                                                double (&acc)[4])
 {
     const int KC = c.KC, KR = c.KR;
@@ -801,7 +850,9 @@ __device__ __forceinline__ void tile_row_edges(const TileCtx& c, const double* _
                 bq[q] = b;
                 const uint32_t orow = row ^ (1u << b);
                 if (on) {
-                    k[q] = c.rowB[b][ADJ ? row : orow];
+                    const uint32_t rr = ADJ ? row : orow;
+                    if constexpr (MODE == TM_WIDE) k[q] = c.rowB[b][(rr >> c.rsh[b]) & c.rmask[b]];
+                    else k[q] = c.rowB[b][rr];
                     ld4(v + (((uint64_t)orow << KC) | lo0), y[q]);
                 } else {
                     k[q] = 0.0;
@@ -811,7 +862,9 @@ __device__ __forceinline__ void tile_row_edges(const TileCtx& c, const double* _
             }
 #pragma unroll
             for (int q = 0; q < NB; ++q) {
-                if (PROD) {
+                bool has_cf = MODE == TM_PROD;
+                if constexpr (MODE == TM_WIDE) has_cf = !c.cfone[bq[q]];
+                if (has_cf) {
                     double cf[4];
                     ld4(c.colB[bq[q]] + lo0, cf);
 #pragma unroll
@@ -826,8 +879,8 @@ __device__ __forceinline__ void tile_row_edges(const TileCtx& c, const double* _
 }
 
 // diagonal, column bits 0,1 (inside the lane) and 2,3 (across the four lanes of a row group): acc -> val
-template <bool ADJ, bool PROD>
-__device__ __forceinline__ void tile_tail(const TileCtx& c, uint32_t row, uint32_t lo0, int lane, double (&acc)[4], double (&val)[4])
+template <bool ADJ, int MODE, class CTX>
+__device__ __forceinline__ void tile_tail(const CTX& c, uint32_t row, uint32_t lo0, int lane, double (&acc)[4], double (&val)[4])
 {
     const int KC = c.KC;
     const int lc = lane & 3;
@@ -836,10 +889,12 @@ __device__ __forceinline__ void tile_tail(const TileCtx& c, uint32_t row, uint32
     double inv[4];
     {
         double d[4];
-        if (PROD) ld4(c.dA + s0, d);
+        if (MODE == TM_PROD) ld4(c.dA + s0, d);
         else {
-            ld4(c.dA + lo0, d);
-            const double k = c.dB[row];
+            uint32_t ia = lo0, ib = row;
+            if constexpr (MODE == TM_WIDE) { ia = s0 & c.mAfull; ib = row >> c.K2A; }
+            ld4(c.dA + ia, d);
+            const double k = c.dB[ib];
 #pragma unroll
             for (int t = 0; t < 4; ++t) d[t] += k;
         }
@@ -848,7 +903,11 @@ __device__ __forceinline__ void tile_tail(const TileCtx& c, uint32_t row, uint32
     }
     // ---- column bits 0,1 (inside the lane) and 2,3 (across the four lanes of the row group) ----
     double k0 = 1.0, k1 = 1.0, k2 = 1.0, k3 = 1.0;
-    if (PROD) { k0 = c.rowA[0][row]; k1 = c.rowA[1][row]; k2 = c.rowA[2][row]; k3 = c.rowA[3][row]; }
+    if (MODE != TM_PAIR) {
+        uint32_t ri = row;
+        if constexpr (MODE == TM_WIDE) ri = row & c.mH;
+        k0 = c.rowA[0][ri]; k1 = c.rowA[1][ri]; k2 = c.rowA[2][ri]; k3 = c.rowA[3][ri];
+    }
     double e0a, e0b, e1a, e1b;
     {
         double q0[4], q1[4];
@@ -918,8 +977,8 @@ __device__ __forceinline__ void tile_tail(const TileCtx& c, uint32_t row, uint32
     fin();
 }
 
-template <bool ADJ, bool PROD>
-__device__ __forceinline__ void solve_tile16(const SpaceDev& sp, const SpaceDev* __restrict__ spaces, const TileCtx& c,
+template <bool ADJ, int MODE, class CTX>
+__device__ __forceinline__ void solve_tile16(const SpaceDev& sp, const SpaceDev* __restrict__ spaces, const CTX& c,
                                              double* __restrict__ S, uint32_t cA, uint32_t row, bool valid, int lane)
 {
     const int KC = c.KC, KR = c.KR;
@@ -928,7 +987,8 @@ __device__ __forceinline__ void solve_tile16(const SpaceDev& sp, const SpaceDev*
     const uint32_t s0 = (row << KC) | lo0;
     double* v = S + (ADJ ? sp.x_off : sp.y_off);
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    tile_rhs<ADJ>(sp, spaces, S, KC, KR, row, lo0, acc);
+    if constexpr (MODE == TM_WIDE) tile_rhs<ADJ, true>(sp, spaces, S, KC, KR, row, lo0, acc, KC + c.K2A, KR - c.K2A);
+    else tile_rhs<ADJ>(sp, spaces, S, KC, KR, row, lo0, acc);
     // Edges are taken NB at a time, all loads of a round before its FMAs: a tile is a chain of dependent rounds and
     // thin levels have no other warps to hide the memory latency behind.
     // ---- column bits >= 4 (uniform over the warp): FWD visits the set bits of cA, ADJ the unset ones ----
@@ -947,7 +1007,8 @@ __device__ __forceinline__ void solve_tile16(const SpaceDev& sp, const SpaceDev*
                 if (on) {
                     ld4(c.colA[a] + (ADJ ? lo0 : (lo0 ^ bit)), r[q]);
                     ld4(v + (s0 ^ bit), y[q]);
-                    if (PROD) k[q] = c.rowA[a][row];
+                    if constexpr (MODE == TM_WIDE) k[q] = c.rowA[a][row & c.mH];
+                    else if (MODE == TM_PROD) k[q] = c.rowA[a][row];
                 } else {
 #pragma unroll
                     for (int t = 0; t < 4; ++t) { r[q][t] = 0.0; y[q][t] = 0.0; }
@@ -956,12 +1017,12 @@ __device__ __forceinline__ void solve_tile16(const SpaceDev& sp, const SpaceDev*
 #pragma unroll
             for (int q = 0; q < NB; ++q)
 #pragma unroll
-                for (int t = 0; t < 4; ++t) acc[t] = fma(PROD ? r[q][t] * k[q] : r[q][t], y[q][t], acc[t]);
+                for (int t = 0; t < 4; ++t) acc[t] = fma(MODE != TM_PAIR ? r[q][t] * k[q] : r[q][t], y[q][t], acc[t]);
         }
     }
-    tile_row_edges<ADJ, PROD>(c, v, row, lo0, acc);
+    tile_row_edges<ADJ, MODE>(c, v, row, lo0, acc);
     double val[4];
-    tile_tail<ADJ, PROD>(c, row, lo0, lane, acc, val);
+    tile_tail<ADJ, MODE>(c, row, lo0, lane, acc, val);
     if (valid) st4(v + s0, val[0], val[1], val[2], val[3]);
 }
 
@@ -990,8 +1051,37 @@ k_solve_tile(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs,
         const bool valid = ri < nB;
         const uint32_t cA = hs[offA + iA];
         const uint32_t row = hs[offB + min(ri, nB - 1u)];
-        if (prod) solve_tile16<ADJ, true>(sp, spaces, ctx, S, cA, row, valid, lane);
-        else      solve_tile16<ADJ, false>(sp, spaces, ctx, S, cA, row, valid, lane);
+        if (prod) solve_tile16<ADJ, TM_PROD>(sp, spaces, ctx, S, cA, row, valid, lane);
+        else      solve_tile16<ADJ, TM_PAIR>(sp, spaces, ctx, S, cA, row, valid, lane);
+    }
+}
+
+// the same for wide pairs (TM_WIDE): a separate kernel, so that its extra index arithmetic stays out of the register
+// budget of the two main paths
+template <bool ADJ>
+__global__ void __launch_bounds__(256, 3)
+k_solve_tile_w(const SpaceDev* __restrict__ spaces, const Item* __restrict__ segs, const uint32_t* __restrict__ hs,
+               const uint32_t* __restrict__ hsidx, double* __restrict__ S)
+{
+    __shared__ TileCtxW ctx;
+    const Item sg = segs[blockIdx.x];
+    const SpaceDev& sp = spaces[sg.space];
+    tile_ctx_build_wide(ctx, sp, S, threadIdx.x);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t lA = sg.a & 255u, lB = (sg.a >> 8) & 255u, cnt = sg.a >> 16;
+    const uint32_t offA = hsidx[(ctx.KC - 4) * 32 + lA];
+    const uint32_t offB = hsidx[ctx.KR * 32 + lB];
+    const uint32_t nB = hsidx[ctx.KR * 32 + lB + 1] - offB;
+    const uint32_t nBg = (nB + 7u) >> 3;
+    for (uint32_t q = w; q < cnt; q += 8) {
+        const uint32_t t = sg.b + q;
+        const uint32_t iA = t / nBg, jB = t - iA * nBg;
+        const uint32_t ri = jB * 8u + (uint32_t)(lane >> 2);
+        const bool valid = ri < nB;
+        const uint32_t cA = hs[offA + iA];
+        const uint32_t row = hs[offB + min(ri, nB - 1u)];
+        solve_tile16<ADJ, TM_WIDE>(sp, spaces, ctx, S, cA, row, valid, lane);
     }
 }
 
@@ -1105,7 +1195,7 @@ k_solve_tile_adjb(const SpaceDev* __restrict__ spaces, const Item* __restrict__ 
             }
         }
         double val[4];
-        tile_tail<true, false>(c, row, lo0, lane, acc, val);
+        tile_tail<true, TM_PAIR>(c, row, lo0, lane, acc, val);
         const double gsum = group4_sum(fma(y4[3], val[3], fma(y4[2], val[2], fma(y4[1], val[1], y4[0] * val[0]))));
         if (lc == 0) pb[q][lg][0] = gsum;
         if (valid) st4(v + s0, val[0], val[1], val[2], val[3]);
