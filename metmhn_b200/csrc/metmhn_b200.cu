@@ -592,9 +592,11 @@ static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_da
                 for (uint32_t u = 0; u < (1u << (sp[i].KA - sp[i].splitA)); u += FIN_U) items.push_back({i, 3u, u});
                 continue;
             }
-            for (uint32_t u = 0; u < (1u << sp[i].KA); u += FIN_U) items.push_back({i, 0u, u});
+            // groups with 2^15 sub-states or more (wide pairs: thousands of items per space) take coarser items
+            const uint32_t UA = sp[i].KA >= 15 ? FIN_U_WIDE : FIN_U, UB = sp[i].KB >= 15 ? FIN_U_WIDE : FIN_U;
+            for (uint32_t u = 0; u < (1u << sp[i].KA); u += UA) items.push_back({i, 0u, u, UA});
             if (sp[i].kind == K_JOINT)
-                for (uint32_t u = 0; u < (1u << sp[i].KB); u += FIN_U) items.push_back({i, 1u, u});
+                for (uint32_t u = 0; u < (1u << sp[i].KB); u += UB) items.push_back({i, 1u, u, UB});
         }
         ck.fin.cnt = (uint32_t)(items.size() - ck.fin.off);
         h->chunks.push_back(std::move(ck));

@@ -24,6 +24,9 @@ constexpr int MAXG    = 26;   // bits per group
 constexpr int BIGK    = 13;   // spaces with K >= BIGK are solved by per-level launches
 constexpr int SEGB    = 32;   // blocks of 32 states per big-tier segment (one CTA)
 constexpr int FIN_U   = 64;   // sub-states per finish work item
+#ifndef FIN_U_WIDE
+#define FIN_U_WIDE 256        // ... of a group with 2^15 sub-states or more (item.c carries the size)
+#endif
 
 enum Kind : uint8_t { K_PRE = 0, K_JOINT = 1, K_PF = 2, K_MF = 3, K_S1 = 4, K_S2 = 5 };
 
@@ -1771,7 +1774,7 @@ k_finish(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, ui
             else       { for (int b = 0; b < KG; ++b) if (ev[b] == lane) abit = b; }
             const bool pre_seed = sp.kind == K_PRE;
             const SpaceDev& jsp = spaces[pre_seed ? sp.joint : it.space];
-            const uint32_t u_end = min(NG, it.b + FIN_U);
+            const uint32_t u_end = min(NG, it.b + (it.c ? it.c : (uint32_t)FIN_U));
             for (uint32_t u0 = it.b; u0 < u_end; u0 += 32) {
                 const uint32_t u = u0 + lane;
                 const bool uv = u < u_end;
