@@ -1470,7 +1470,7 @@ k_stats_b(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, u
 // Row metadata shared by the three kernels below: for table row r of a product-form space
 //   kind 0: unused   1: event absent in this patient (or a diagnosis pseudo row)   2: event on lo bit `bit`
 //   3: event on hi bit `bit`
-struct PfRows { int8_t kind[NR], bit[NR]; };
+struct PfRows { int8_t kind[NR], bit[NR], act[NR]; int n_act; };   // act: the rows in use, events of the patient first
 __device__ __forceinline__ void pf_rows_build(PfRows& m, const SpaceDev& sp, int t)
 {
     if (t >= NR) return;
@@ -1482,6 +1482,13 @@ __device__ __forceinline__ void pf_rows_build(PfRows& m, const SpaceDev& sp, int
         for (int b = 0; b < sp.KA; ++b)
             if (sp.evA[b] == t) { kind = b < K1 ? 2 : 3; bit = b < K1 ? b : b - K1; }
     m.kind[t] = (int8_t)kind; m.bit[t] = (int8_t)bit;
+    // compact list of the rows in use (called by the first warp of the CTA): rows of present events (one neighbour load per
+    // state each) first, then absent events / pseudo rows, so that dealing the list round-robin balances the warps of k_pf
+    const unsigned mp = __ballot_sync(0xffffffffu, kind >= 2), mo = __ballot_sync(0xffffffffu, kind == 1);
+    const unsigned below = (1u << t) - 1u;
+    if (kind >= 2) m.act[__popc(mp & below)] = (int8_t)t;
+    else if (kind == 1) m.act[__popc(mp) + __popc(mo & below)] = (int8_t)t;
+    if (t == 0) m.n_act = __popc(mp) + __popc(mo);
 }
 
 // Diagonal of a product-form space (replaces the per-state 26-term loop of the first version):
@@ -1641,15 +1648,17 @@ k_pf(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, double
     const double* y = S + sp.y_off;
     const double* T1 = S + sp.tabA;
     const double* T2 = T1 + ((uint64_t)NR << K1);
-    int kind[PF_RW], bit[PF_RW];
+    int kind[PF_RW], bit[PF_RW], row[PF_RW];              // the rows in use are dealt round-robin to the warps
     double acc[PF_RW][4], tvr[PF_RW][4];
 #pragma unroll
     for (int j = 0; j < PF_RW; ++j) {
-        kind[j] = live ? rows.kind[rg * PF_RW + j] : 0;
-        bit[j] = rows.bit[rg * PF_RW + j];
+        const int slot = rg + PF_WARPS * j;
+        row[j] = slot < rows.n_act ? rows.act[slot] : 0;
+        kind[j] = (live && slot < rows.n_act) ? rows.kind[row[j]] : 0;
+        bit[j] = rows.bit[row[j]];
 #pragma unroll
         for (int t = 0; t < 4; ++t) { acc[j][t] = 0.0; tvr[j][t] = 0.0; }
-        if (kind[j] != 0) ld4(T1 + ((uint64_t)(rg * PF_RW + j) << K1) + lo0, tvr[j]);
+        if (kind[j] != 0) ld4(T1 + ((uint64_t)row[j] << K1) + lo0, tvr[j]);
     }
     const bool any_row = (kind[0] | kind[1] | kind[2] | kind[3]) != 0;     // warps without a live row skip the loads
     double* out2 = S + sp.stP + (uint64_t)sp.slices * (NR + KA) * N1 + (uint64_t)it.a * (NR + KA) * N2;
@@ -1674,7 +1683,7 @@ k_pf(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, double
                     bool zero;
                     pf_E(kind[j], bit[j], hi, lo0, K1, x, xv, yv, ng, e, zero);
                     if (zero) continue;
-                    const double tw = T2[((uint64_t)(rg * PF_RW + j) << K2) + hi];
+                    const double tw = T2[((uint64_t)row[j] << K2) + hi];
 #pragma unroll
                     for (int t = 0; t < 4; ++t) acc[j][t] = fma(tw, e[t], acc[j][t]);
                     p[j] = fma(tvr[j][3], e[3], fma(tvr[j][2], e[2], fma(tvr[j][1], e[1], tvr[j][0] * e[0])));
@@ -1689,14 +1698,15 @@ k_pf(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, double
 #pragma unroll
             for (int l = 0; l < 32; ++l) s += red[rg][lane][l];
             const int j = lane / PF_HBATCH, hh = lane % PF_HBATCH;
-            if (hb + hh < h1) out2[(uint64_t)(rg * PF_RW + j) * N2 + hb + hh] = s;
+            if (hb + hh < h1 && rg + PF_WARPS * j < rows.n_act) out2[(uint64_t)rows.act[rg + PF_WARPS * j] * N2 + hb + hh] = s;
         }
         __syncwarp();
     }
     if (!live) return;
     double* out = S + sp.stP + (uint64_t)it.b * (NR + KA) * N1;
 #pragma unroll
-    for (int j = 0; j < PF_RW; ++j) st4(out + (uint64_t)(rg * PF_RW + j) * N1 + lo0, acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+    for (int j = 0; j < PF_RW; ++j)
+        if (rg + PF_WARPS * j < rows.n_act) st4(out + (uint64_t)row[j] * N1 + lo0, acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
 }
 // ------------------------------------------------------------------------------------------
 // Gradient contraction.  For event row i and sub-state u of a group (i not in u)
