@@ -42,7 +42,7 @@ struct ChunkPlan {
     uint32_t nspaces = 0;
     Range pre4, main_small4, sec_small4;         // small-tier spaces with K >= 7 (four states per lane)
     Range rb_list;                               // pairs of the row-block kernel
-    Range setup, setup_wide, diag, pre, main_small, sec_small, logp, joints, st_a, st_ar, st_b, pf_lo, fin;
+    Range setup, setup_wide, diag, pre, main_small, sec_small, logp, joints, st_a, st_ar, st_b, st_bn, pf_lo, fin;
     bool wide = false;                           // some group has more than MAXT bits
     std::vector<Range> main_lv, sec_lv;          // big-tier segments per popcount level (generic kernel)
     std::vector<Range> main_lvt, sec_lvt;        // big-tier tiles per level (tiled kernel)
@@ -130,6 +130,9 @@ static uint32_t adjb_slots(int kbA, uint32_t* base)
     return n;
 }
 
+// pairs whose group-B statistics are taken one lane per row (k_stats_b_narrow)
+static bool narrow_b(const SpaceDev& s) { return s.kind == K_JOINT && !fused_b(s) && s.KA <= STB_NARROW; }
+
 static uint64_t space_scratch(SpaceDev& s, uint64_t off)
 {
     const uint64_t NA = 1ull << s.KA, NB = 1ull << s.KB, N = NA * NB;
@@ -160,6 +163,7 @@ static uint64_t space_scratch(SpaceDev& s, uint64_t off)
         s.slicesB = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(256, capB), std::max<uint64_t>(1, NA / 2048));
         if (fused_b(s)) s.slicesB = adjb_slots(s.KA - 4, nullptr);     // one partial table per (lA, column chunk)
         if (rb_space(s)) s.slicesB = 1u << std::max(0, (int)s.KA - RB_KI);   // one per value of the outer column bits
+        if (narrow_b(s)) s.slicesB = 1;
         s.stA = take((s.KA + 1) * NA);
         s.stB = take((s.KB + 1) * NB);
         s.stP = take((uint64_t)s.slices * (s.KA + 1) * NA);
@@ -573,10 +577,15 @@ static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_da
         ck.st_ar.cnt = (uint32_t)(items.size() - ck.st_ar.off);
         ck.st_b.off = items.size();
         for (uint32_t i = 0; i < ck.nspaces; ++i)
-            if (sp[i].kind == K_JOINT && !fused_b(sp[i]))
+            if (sp[i].kind == K_JOINT && !fused_b(sp[i]) && !narrow_b(sp[i]))
                 for (uint32_t sl = 0; sl < sp[i].slicesB; ++sl)
                     for (uint32_t u = 0; u < (1u << sp[i].KB); ++u) items.push_back({i, u, sl});
         ck.st_b.cnt = (uint32_t)(items.size() - ck.st_b.off);
+        ck.st_bn.off = items.size();
+        for (uint32_t i = 0; i < ck.nspaces; ++i)
+            if (narrow_b(sp[i]))
+                for (uint32_t u = 0; u < (1u << sp[i].KB); u += 32) items.push_back({i, u, 0u});
+        ck.st_bn.cnt = (uint32_t)(items.size() - ck.st_bn.off);
         ck.pf_lo.off = items.size();
         for (uint32_t i = 0; i < ck.nspaces; ++i)
             if (is_prod(sp[i])) {
@@ -809,6 +818,7 @@ static int enqueue_eval(mmh_handle* h, const double* d_params, double w0, double
         if (ck.st_a.cnt) {
             k_stats_a<<<(ck.st_a.cnt + 7) / 8, 256, 0, st>>>(sp, h->d_items + ck.st_a.off, ck.st_a.cnt, S);
             if (ck.st_b.cnt) k_stats_b<<<(ck.st_b.cnt + 7) / 8, 256, 0, st>>>(sp, h->d_items + ck.st_b.off, ck.st_b.cnt, S);
+            if (ck.st_bn.cnt) { k_stats_b_narrow<<<(ck.st_bn.cnt + 7) / 8, 256, 0, st>>>(sp, h->d_items + ck.st_bn.off, ck.st_bn.cnt, S); ++launches; }
             k_stats_reduce<<<ck.st_ar.cnt, 1024, 0, st>>>(sp, h->d_items + ck.st_ar.off, S);
             launches += 3;
         }

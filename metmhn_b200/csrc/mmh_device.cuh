@@ -1464,6 +1464,41 @@ k_stats_b(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, u
     }
 }
 
+// group-B statistics of pairs with at most STB_NARROW PT bits (small pairs, and pairs whose PT has almost no events): a row
+// has at most 32 columns, a warp per row would idle most of its lanes -- one LANE per uB instead, the row sums run in the
+// lane.  One partial table (slot 0).   item: a = first uB of 32
+constexpr int STB_NARROW = 5;
+__global__ void __launch_bounds__(256)
+k_stats_b_narrow(const SpaceDev* __restrict__ spaces, const Item* __restrict__ items, uint32_t count, double* __restrict__ S)
+{
+    const uint32_t wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wg >= count) return;
+    const Item it = items[wg];
+    const SpaceDev& sp = spaces[it.space];
+    const int KA = sp.KA, KB = sp.KB;
+    const uint32_t NA = 1u << KA, NB = 1u << KB;
+    const uint32_t uB = it.a + (uint32_t)lane;
+    if (uB >= NB) return;
+    const double* yr = S + sp.y_off + ((uint64_t)uB << KA);
+    const double* xb = S + sp.x_off;
+    double* out = S + sp.stPB;
+    {
+        const double* xr = xb + ((uint64_t)uB << KA);
+        double g = 0.0;
+        for (uint32_t i = 0; i < NA; ++i) g = fma(yr[i], xr[i], g);
+        out[uB] = g;
+    }
+    for (int b = 0; b < KB; ++b) {
+        double s = 0.0;
+        if (!((uB >> b) & 1u)) {
+            const double* xr = xb + ((uint64_t)(uB | (1u << b)) << KA);
+            for (uint32_t i = 0; i < NA; ++i) s = fma(yr[i], xr[i], s);
+        }
+        out[(uint64_t)(1 + b) * NB + uB] = s;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Single-tumour spaces in product form (K1 low bits "lo", K2 high bits "hi"; rate(r,u) = T1[r][lo] T2[r][hi]).
 //
