@@ -424,7 +424,7 @@ static int create_impl(mmh_handle* h, int n_mut, const int8_t* dat, int64_t n_da
                     for (uint32_t lb = 0; lb < nlo; ++lb) items.push_back({i, lb, hb});
             }
         ck.diag.cnt = (uint32_t)(items.size() - ck.diag.off);
-        // spaces the tiled solve kernel takes (must agree with tiled_space() on the device side)
+        // spaces the tile solve kernels take (k_solve_tile / k_solve_tile_adjb / k_solve_tile_w)
         auto tiled = [&](const SpaceDev& s) {
             if (bits(s) < BIGK || s.kind == K_PRE || rb_space(s)) return false;
             static const bool wide_on = [] { const char* e = std::getenv("MMH_WIDE_TILE"); return !e || std::atoi(e) != 0; }();

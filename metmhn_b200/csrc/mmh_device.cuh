@@ -740,13 +740,6 @@ struct TileCtxW : TileCtx {
 // 31 % of the n = 20 / 10 000 step, 28 were 7 % of the n = 25 / 100 000 step (scripts/marginal_generic.py).
 constexpr int TM_PAIR = 0, TM_PROD = 1, TM_WIDE = 2;
 
-__device__ __forceinline__ bool tiled_space(const SpaceDev& sp)
-{
-    if ((int)sp.KA + (int)sp.KB < BIGK || sp.kind == K_PRE) return false;
-    if (sp.kind == K_JOINT) return !sp.splitB && (sp.splitA ? sp.splitA >= 4 : sp.KA >= 4);
-    return sp.splitA >= 4;
-}
-__device__ __forceinline__ bool wide_tiled_space(const SpaceDev& sp) { return sp.kind == K_JOINT && sp.splitA != 0; }
 
 __device__ __forceinline__ void tile_ctx_build(TileCtx& c, const SpaceDev& sp, const double* __restrict__ S, int t)
 {
