@@ -185,11 +185,10 @@ __global__ void k_setup(const SpaceDev* __restrict__ spaces, const Item* __restr
     for (int i = 0; i < sel.nrows; ++i) {
         double r = part ? 1.0 : P->base[sel.bid][i];
         bool in_u = false;
-        for (int b = 0; b < KT; ++b)
-            if ((u >> b) & 1u) {
-                const int e = sev[b];
-                if (e == i) in_u = true; else r *= P->W[sel.wid][i][e];
-            }
+        for (uint32_t m = u; m; m &= m - 1) {                  // set bits only, in ascending order (same product as before)
+            const int e = sev[__ffs(m) - 1];
+            if (e == i) in_u = true; else r *= P->W[sel.wid][i][e];
+        }
         tab[(uint64_t)i * NT + u] = r;
         if (!in_u) dsum += r;
     }
@@ -1387,7 +1386,15 @@ __global__ void k_stats_reduce(const SpaceDev* __restrict__ spaces, const Item* 
     const uint32_t ns = it.a ? sp.slicesB : sp.slices;
     const double* src = S + (it.a ? sp.stPB : sp.stP);
     double s = 0.0;
-    for (uint32_t k = 0; k < ns; ++k) s += src[k * len + t];
+    uint32_t k = 0;
+    for (; k + 8 <= ns; k += 8) {                            // eight loads in flight, added in slot order
+        double v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = src[(uint64_t)(k + q) * len + t];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s += v[q];
+    }
+    for (; k < ns; ++k) s += src[(uint64_t)k * len + t];
     S[(it.a ? sp.stB : sp.stA) + t] = s;
 }
 

@@ -104,3 +104,29 @@ def test_two_formulations_agree_on_mid_size_spaces():
         assert abs(o1[1] - o2[1]) <= TOL * abs(o1[1])
         for x, y in zip(o1[2:], o2[2:]):
             assert rel_err(y, x) <= TOL
+
+
+def test_lattice_oracle_matches_reference_on_big_lattices():
+    """tests/golden/golden_big.npz: rows of the bench datasets with 2^13 ... 2^18-state lattices evaluated by the UNMODIFIED
+    reference under the shim (tests/golden/make_golden_big.py, hours of CPU).  The lattice formulation -- the checker of
+    the big-tier GPU tests -- reproduces them, so the oracle chain is pinned to the reference where the time goes."""
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_big.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/golden_big.npz has not been generated")
+    gb = np.load(path)
+    checked = 0
+    for c in [str(x) for x in gb["cases"]]:
+        rows, ep = gb[f"{c}/rows"], gb[f"{c}/eval_point"]
+        n_tot = (rows.shape[1] - 3) // 2 + 1
+        th, dp, dm = ep[:n_tot * n_tot].reshape(n_tot, n_tot), ep[n_tot * n_tot:n_tot * n_tot + n_tot], ep[n_tot * n_tot + n_tot:]
+        bits = rows[:, :2 * (n_tot - 1) + 1].astype(int).sum(axis=1)
+        for r in np.nonzero(bits <= 16)[0]:                      # seconds in total; the 2^18-state rows are left to the GPU test
+            out = ld.patient_value_grad(th, dp, dm, rows[r])
+            ref = gb[f"{c}/row_logp"][r]
+            assert abs(out[1] - ref) <= TOL * abs(ref), (c, r)
+            assert rel_err(out[2], gb[f"{c}/row_g"][r]) <= TOL, (c, r)
+            assert rel_err(out[3], gb[f"{c}/row_gdp"][r]) <= TOL, (c, r)
+            assert rel_err(out[4], gb[f"{c}/row_gdm"][r]) <= TOL, (c, r)
+            checked += 1
+    assert checked >= 10
