@@ -126,6 +126,9 @@ int mmh_multi_create(mmh_multi** out, int n_mut, const int8_t* dat, int64_t n_da
 int mmh_multi_value_grad(mmh_multi* m, const double* params, double perc_met, double* score, double* grad);
 int mmh_multi_value(mmh_multi* m, const double* params, double perc_met, double* score);
 void mmh_multi_destroy(mmh_multi* m);
+/* The partition's work estimate of one row (lattice states times the measured cost per state of the row's kind and size,
+ * picoseconds on a B200); pure host arithmetic, no device needed.  metmhn_b200/sharded.py: patient_cost is the same table. */
+double mmh_row_cost(const int8_t* row, int n_mut);
 
 /* learn_mhn (regularized_optimization.py:301-334) as ONE call: minimises -score + w_penal * symmetric_penal(params)
  * (:46-52, smoothing eps, 1e-5 in the reference) from x0 with L-BFGS-B without bounds (m = 10, More'-Thuente line search,

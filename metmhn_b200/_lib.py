@@ -22,7 +22,8 @@ EXPORTS = ("mmh_create", "mmh_value_grad", "mmh_value", "mmh_eval_weighted", "mm
            "mmh_set_profile", "mmh_per_patient",
            "mmh_stats", "mmh_destroy", "mmh_last_error", "mmh_measure_fp64_tflops",
            "mmh_nccl_unique_id", "mmh_comm_init", "mmh_comm_destroy",
-           "mmh_multi_create", "mmh_multi_value_grad", "mmh_multi_value", "mmh_multi_destroy", "mmh_simulate", "mmh_learn", "mmh_per_patient_grads")
+           "mmh_multi_create", "mmh_multi_value_grad", "mmh_multi_value", "mmh_multi_destroy", "mmh_simulate", "mmh_learn", "mmh_per_patient_grads",
+           "mmh_row_cost")
 
 
 class Stats(C.Structure):
@@ -77,8 +78,10 @@ def lib():
     L.mmh_learn.argtypes = [C.c_void_p, dp, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_double, dp, dp,
                             C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     for name in EXPORTS:
-        if name not in ("mmh_destroy", "mmh_last_error", "mmh_multi_destroy"):
+        if name not in ("mmh_destroy", "mmh_last_error", "mmh_multi_destroy", "mmh_row_cost"):
             getattr(L, name).restype = C.c_int
+    L.mmh_row_cost.restype = C.c_double
+    L.mmh_row_cost.argtypes = [C.c_void_p, C.c_int]
     _lib = L
     return L
 

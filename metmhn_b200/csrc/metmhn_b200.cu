@@ -1184,6 +1184,11 @@ static double row_cost(const int8_t* row, int n)
     return 1.0;
 }
 
+extern "C" double mmh_row_cost(const int8_t* row, int n_mut)
+{
+    return (row && n_mut >= 1 && n_mut <= MMH_MAX_MUT) ? row_cost(row, n_mut) : 0.0;
+}
+
 extern "C" void mmh_multi_destroy(mmh_multi* m)
 {
     if (!m) return;

@@ -44,6 +44,23 @@ def test_rebalance_moves_shift_load_from_slow_to_fast_ranks():
     assert np.array_equal(rebalance_moves(a0, cost, np.ones(4)), a0)                   # balanced: nothing moves
 
 
+def test_library_cost_model_equals_the_python_one():
+    """`row_cost` of the library (partition of mmh_multi_create) and `patient_cost` (ShardedEvaluator) are the same table."""
+    import ctypes as C
+    import os
+    lib = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "metmhn_b200", "libmetmhn_b200.so")
+    if not os.path.exists(lib):
+        pytest.skip("library not built")
+    L = C.CDLL(lib)
+    L.mmh_row_cost.restype = C.c_double
+    L.mmh_row_cost.argtypes = [C.c_void_p, C.c_int]
+    for n, nd, seed in ((12, 400, 5), (20, 300, 7), (25, 300, 9)):
+        dat = np.ascontiguousarray(syn_v1(n, nd, seed)["dat"], dtype=np.int8)
+        want = patient_cost(dat)
+        got = np.array([L.mmh_row_cost(dat[r].ctypes.data, n) for r in range(dat.shape[0])])
+        assert np.array_equal(got, want)
+
+
 def test_class_weights_match_reference_formula():
     w0, w1 = class_weights(100, 80, 0.65)
     w = 0.65 * 20 / (0.35 * 80)
